@@ -1,0 +1,222 @@
+/*
+ * libm_f32.h -- float sin/cos/log evaluated in IEEE binary64, for host AND device.
+ *
+ * Why this exists: the reference computes its NCO with Rust `f32::sin_cos`
+ * (/root/reference/src/modem/modulator.rs:46) and `f32::cos` / `f32::sin`
+ * (/root/reference/src/modem/demodulator.rs:53-54), which lower to the platform
+ * libm `sinf` / `cosf`.  CUDA's `sinf/cosf` are 1-2 ULP routines and are NOT
+ * bit-identical to that.  B200 has a full-rate FP64 pipe (half the FP32 rate), so
+ * we evaluate the same published algorithm the platform libm uses -- the
+ * "optimized-routines" single-precision sincosf / logf (range reduction by pi/2 in
+ * binary64, two short binary64 polynomials, one final rounding to binary32) -- with
+ * the same constants and the same operation order.  Every operation is a correctly
+ * rounded IEEE binary64 op on both sides, so the result is bit-identical to glibc
+ * 2.39 `sinf/cosf/logf` (verified exhaustively on the host by tools/check_libm.c;
+ * the same header is what the kernels compile).
+ *
+ * MG_LIBM_CONTRACT selects whether `a*b+c` is one fused op or two rounded ops.
+ * x86-64 glibc dispatches (ifunc) to an FMA build of these routines on every CPU
+ * that has FMA, so the default is 1.
+ */
+#ifndef MODEM_GPU_LIBM_F32_H
+#define MODEM_GPU_LIBM_F32_H
+
+#include <stdint.h>
+
+#ifndef MG_LIBM_CONTRACT
+#define MG_LIBM_CONTRACT 1
+#endif
+
+#if defined(__CUDACC__)
+#define MG_HD __host__ __device__ __forceinline__
+#else
+#define MG_HD static inline
+#endif
+
+#if defined(__CUDA_ARCH__)
+#define MG_DMUL(a, b) __dmul_rn((a), (b))
+#define MG_DADD(a, b) __dadd_rn((a), (b))
+#if MG_LIBM_CONTRACT
+#define MG_DFMA(a, b, c) __fma_rn((a), (b), (c))
+#else
+#define MG_DFMA(a, b, c) __dadd_rn(__dmul_rn((a), (b)), (c))
+#endif
+#define MG_ASUINT(f) __float_as_uint(f)
+#define MG_ASFLOAT(u) __uint_as_float(u)
+#else
+#include <string.h>
+#include <math.h>
+static inline double mg_host_mul(double a, double b) { volatile double r = a * b; return r; }
+#define MG_DMUL(a, b) ((a) * (b))
+#define MG_DADD(a, b) ((a) + (b))
+#if MG_LIBM_CONTRACT
+#define MG_DFMA(a, b, c) __builtin_fma((a), (b), (c))
+#else
+/* the volatile round-trip forbids the host compiler from fusing */
+#define MG_DFMA(a, b, c) (mg_host_mul((a), (b)) + (c))
+#endif
+static inline uint32_t mg_asuint_host(float f) { uint32_t u; memcpy(&u, &f, 4); return u; }
+static inline float mg_asfloat_host(uint32_t u) { float f; memcpy(&f, &u, 4); return f; }
+#define MG_ASUINT(f) mg_asuint_host(f)
+#define MG_ASFLOAT(u) mg_asfloat_host(u)
+#endif
+
+/* ---- constants (hex floats: exact) ------------------------------------------- */
+#define MG_HPI_INV_2P24 0x1.45F306DC9C883p+23 /* 2/pi * 2^24 */
+#define MG_HPI 0x1.921FB54442D18p0            /* pi/2 */
+#define MG_C0 0x1p0
+#define MG_C1 (-0x1.ffffffd0c621cp-2)
+#define MG_C2 0x1.55553e1068f19p-5
+#define MG_C3 (-0x1.6c087e89a359dp-10)
+#define MG_C4 0x1.99343027bf8c3p-16
+#define MG_S1 (-0x1.555545995a603p-3)
+#define MG_S2 0x1.1107605230bc4p-7
+#define MG_S3 (-0x1.994eb3774cf24p-13)
+
+MG_HD uint32_t mg_abstop12(float x) { return (MG_ASUINT(x) >> 20) & 0x7ff; }
+
+/*
+ * Both polynomials on reduced argument x (|x| <= pi/4), x2 = x*x.
+ * `neg` selects the sign-flipped cosine coefficient set (quadrants 2,3).
+ */
+MG_HD void mg_sincos_poly(double x, double x2, int neg, int n, float* sinp, float* cosp)
+{
+    const double c0 = neg ? -MG_C0 : MG_C0;
+    const double c1 = neg ? -MG_C1 : MG_C1;
+    const double c2k = neg ? -MG_C2 : MG_C2;
+    const double c3 = neg ? -MG_C3 : MG_C3;
+    const double c4 = neg ? -MG_C4 : MG_C4;
+
+    double x4 = MG_DMUL(x2, x2);
+    double x3 = MG_DMUL(x2, x);
+    double c2 = MG_DFMA(x2, c4, c3);
+    double s1 = MG_DFMA(x2, MG_S3, MG_S2);
+    double c1v = MG_DFMA(x2, c1, c0);
+    double x5 = MG_DMUL(x3, x2);
+    double x6 = MG_DMUL(x4, x2);
+    double s = MG_DFMA(x3, MG_S1, x);
+    double c = MG_DFMA(x4, c2k, c1v);
+    float sv = (float)MG_DFMA(x5, s1, s);
+    float cv = (float)MG_DFMA(x6, c2, c);
+    if (n & 1) {
+        *cosp = sv;
+        *sinp = cv;
+    } else {
+        *sinp = sv;
+        *cosp = cv;
+    }
+}
+
+/* 4/pi as overlapping 32-bit words, for |y| >= 120 (Payne-Hanek style). */
+#if defined(__CUDA_ARCH__)
+__device__ __constant__ uint32_t mg_inv_pio4[24] = {
+#else
+static const uint32_t mg_inv_pio4[24] = {
+#endif
+    0xa2,       0xa2f9,     0xa2f983,   0xa2f9836e, 0xf9836e4e, 0x836e4e44, 0x6e4e4415, 0x4e441529,
+    0x441529fc, 0x1529fc27, 0x29fc2757, 0xfc2757d1, 0x2757d1f5, 0x57d1f534, 0xd1f534dd, 0xf534ddc0,
+    0x34ddc0db, 0xddc0db62, 0xc0db6295, 0xdb629599, 0x6295993c, 0x95993c43, 0x993c4390, 0x3c439041};
+
+MG_HD double mg_reduce_large(uint32_t xi, int* np)
+{
+    const uint32_t* arr = &mg_inv_pio4[(xi >> 26) & 15];
+    int shift = (xi >> 23) & 7;
+    uint64_t n, res0, res1, res2;
+
+    xi = (xi & 0xffffff) | 0x800000;
+    xi <<= shift;
+
+    res0 = (uint64_t)xi * arr[0];
+    res1 = (uint64_t)xi * arr[4];
+    res2 = (uint64_t)xi * arr[8];
+    res0 = (res2 >> 32) | (res0 << 32);
+    res0 += res1;
+
+    n = (res0 + (1ULL << 61)) >> 62;
+    res0 -= n << 62;
+    double x = (double)(int64_t)res0;
+    *np = (int)n;
+    return MG_DMUL(x, 0x1.921FB54442D18p-62);
+}
+
+/* sinf and cosf of y in one go; same values as separate sinf(y), cosf(y). */
+MG_HD void mg_sincosf(float y, float* sinp, float* cosp)
+{
+    double x = (double)y;
+    int n;
+    uint32_t top = mg_abstop12(y);
+
+    if (top < 0x3f4) { /* |y| < pi/4  (abstop12(0x1.921FB6p-1f) == 0x3f4) */
+        double x2 = MG_DMUL(x, x);
+        if (top < 0x398) { /* |y| < 2^-12 */
+            *sinp = y;
+            *cosp = 1.0f;
+            return;
+        }
+        mg_sincos_poly(x, x2, 0, 0, sinp, cosp);
+    } else if (top < 0x42f) { /* |y| < 120 */
+        double r = MG_DMUL(x, MG_HPI_INV_2P24);
+        n = ((int32_t)r + 0x800000) >> 24;
+        x = MG_DFMA(-(double)n, MG_HPI, x);
+        double s = ((n & 3) == 1 || (n & 3) == 2) ? -1.0 : 1.0;
+        mg_sincos_poly(MG_DMUL(x, s), MG_DMUL(x, x), (n & 2) != 0, n, sinp, cosp);
+    } else if (top < 0x7f8) {
+        uint32_t xi = MG_ASUINT(y);
+        int sign = (int)(xi >> 31);
+        x = mg_reduce_large(xi, &n);
+        int q = (n + sign) & 3;
+        double s = (q == 1 || q == 2) ? -1.0 : 1.0;
+        mg_sincos_poly(MG_DMUL(x, s), MG_DMUL(x, x), (q & 2) != 0, n, sinp, cosp);
+    } else {
+        *sinp = *cosp = y - y;
+    }
+}
+
+/* ---- logf ------------------------------------------------------------------ */
+#if defined(__CUDA_ARCH__)
+__device__ __constant__ double mg_logf_tab[16][2] = {
+#else
+static const double mg_logf_tab[16][2] = {
+#endif
+    {0x1.661ec79f8f3bep+0, -0x1.57bf7808caadep-2}, {0x1.571ed4aaf883dp+0, -0x1.2bef0a7c06ddbp-2},
+    {0x1.49539f0f010bp+0, -0x1.01eae7f513a67p-2},  {0x1.3c995b0b80385p+0, -0x1.b31d8a68224e9p-3},
+    {0x1.30d190c8864a5p+0, -0x1.6574f0ac07758p-3}, {0x1.25e227b0b8eap+0, -0x1.1aa2bc79c81p-3},
+    {0x1.1bb4a4a1a343fp+0, -0x1.a4e76ce8c0e5ep-4}, {0x1.12358f08ae5bap+0, -0x1.1973c5a611cccp-4},
+    {0x1.0953f419900a7p+0, -0x1.252f438e10c1ep-5}, {0x1p+0, 0x0p+0},
+    {0x1.e608cfd9a47acp-1, 0x1.aa5aa5df25984p-5},  {0x1.ca4b31f026aap-1, 0x1.c5e53aa362eb4p-4},
+    {0x1.b2036576afce6p-1, 0x1.526e57720db08p-3},  {0x1.9c2d163a1aa2dp-1, 0x1.bc2860d22477p-3},
+    {0x1.886e6037841edp-1, 0x1.1058bc8a07ee1p-2},  {0x1.767dcf5534862p-1, 0x1.4043057b6ee09p-2}};
+
+#define MG_LN2 0x1.62e42fefa39efp-1
+#define MG_LA0 (-0x1.00ea348b88334p-2)
+#define MG_LA1 0x1.5575b0be00b6ap-2
+#define MG_LA2 (-0x1.ffffef20a4123p-2)
+
+/* logf for finite x > 0 (the only domain the Box-Muller stage feeds it). */
+MG_HD float mg_logf_pos(float x)
+{
+    uint32_t ix = MG_ASUINT(x);
+    if (ix == 0x3f800000u) return 0.0f;
+    if (ix - 0x00800000u >= 0x7f800000u - 0x00800000u) {
+        /* subnormal (callers never pass 0, negatives, inf or nan) */
+        ix = MG_ASUINT(x * 0x1p23f);
+        ix -= 23u << 23;
+    }
+    uint32_t tmp = ix - 0x3f330000u;
+    int i = (int)((tmp >> 19) & 15u);
+    int k = (int32_t)tmp >> 23;
+    uint32_t iz = ix - (tmp & (0x1ffu << 23));
+    double invc = mg_logf_tab[i][0];
+    double logc = mg_logf_tab[i][1];
+    double z = (double)MG_ASFLOAT(iz);
+
+    double r = MG_DFMA(z, invc, -1.0);
+    double y0 = MG_DFMA((double)k, MG_LN2, logc);
+    double r2 = MG_DMUL(r, r);
+    double y = MG_DFMA(MG_LA1, r, MG_LA2);
+    y = MG_DFMA(MG_LA0, r2, y);
+    y = MG_DFMA(y, r2, MG_DADD(y0, r));
+    return (float)y;
+}
+
+#endif /* MODEM_GPU_LIBM_F32_H */
