@@ -1,0 +1,209 @@
+/*
+ * modem_gpu.h -- C ABI of the B200 (sm_100a) batched modulate -> (AWGN) -> demodulate path.
+ *
+ * The reference (ramtej/rust-modem, paths below relative to /root/reference/) has no FFI
+ * or plugin interface; the boundary it offers is the public Rust API of crate `modem`
+ * as used by src/bin/{modulate,demodulate}.rs.  This header is what a thin Rust module
+ * (`modem::gpu`, see INTEGRATION.md and rust-modem_b200/rust/) binds with `extern "C"`,
+ * what the C++ mirror of that API (rust-modem_b200/host/modem.hpp) calls, and what the
+ * Python tests/bench call through ctypes -- the same symbols for all three.
+ *
+ * Conventions
+ *  - plain pointers and sizes only; every entry returns int (0 = MODEM_OK, <0 = error);
+ *    nothing throws or aborts across this boundary.  The Rust side turns a non-zero
+ *    return into the panic!/assert! the reference would raise (e.g. modulate.rs:94).
+ *  - the caller owns every buffer.  Data pointers may be DEVICE pointers (used in place)
+ *    or HOST pointers (pageable or pinned; staged through the context's own device
+ *    scratch with async copies on the context's streams).
+ *  - one context = one device + one stream; a context is not thread-safe, separate
+ *    contexts are independent.
+ *  - frames are independent: the NCO sample counter restarts at cfg.sample0 for each
+ *    frame (a fresh Carrier::new has sample = 0, carrier.rs:10-15) and the FIR history
+ *    starts at zero (fir.rs:13).
+ *  - there is no CPU fallback: every compute entry fails with MODEM_ERR_NO_DEVICE /
+ *    MODEM_ERR_CUDA when no sm_100 device is usable.
+ */
+#ifndef MODEM_GPU_H
+#define MODEM_GPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MODEM_GPU_ABI_VERSION 1
+
+enum {
+    MODEM_OK = 0,
+    MODEM_ERR_INVALID = -1,     /* bad argument / configuration (reference: assert!/panic!) */
+    MODEM_ERR_CUDA = -2,        /* a CUDA runtime call failed; see modem_gpu_last_error */
+    MODEM_ERR_NOMEM = -3,
+    MODEM_ERR_UNSUPPORTED = -4,
+    MODEM_ERR_NCCL = -5,
+    MODEM_ERR_NO_DEVICE = -6
+};
+
+/* num::Complex32 / float2: the sample type of modulator.rs:45-48 and demodulator.rs:8 */
+typedef struct {
+    float re, im;
+} modem_c32_t;
+
+typedef struct modem_ctx modem_ctx_t;
+typedef struct modem_comm modem_comm_t;
+
+/* cfg.flags */
+#define MODEM_FLAG_FUSED_MAC 0x1u /* FIR accumulates with FMA instead of the reference's
+                                     separate mul+add (fir.rs:23).  Faster on long taps, no
+                                     longer bit-identical to the CPU path (still << 1e-5). */
+
+/*
+ * Path configuration.  Field names follow the reference's parameter vocabulary.
+ */
+typedef struct {
+    uint32_t struct_size;        /* = sizeof(modem_cfg_t); ABI guard */
+    uint32_t bits_per_symbol;    /* DigitalPhasor::bits_per_symbol() (digital/phasor.rs:2), 1..8 */
+    uint32_t samples_per_symbol; /* Rates::samples_per_symbol (rates.rs:16) */
+    uint32_t n_tables;           /* 1; 2 for dcqpsk (dcqpsk.rs:42-44): symbol k uses table k % n_tables */
+    const float* const_iq;       /* [n_tables][2^bps][2] (i,q) per symbol index (MSB-first bits,
+                                    digital/util.rs:5-11), from the mapper formulas digital/<scheme>.rs */
+    uint32_t q_offset;           /* EvenOddOffset (data.rs:81-123): Q bit of a symbol is applied this
+                                    many samples late (sps/2 for oqpsk); 0 otherwise.  Needs bps == 2. */
+    float sample_freq;           /* Freq::sample_freq() (freq.rs:24-26), radians per sample */
+    float phase_offset;          /* PLL::phase_offset (pll.rs:6) held for the whole call; 0 = coherent */
+    uint64_t sample0;            /* Carrier.sample at the first sample of every frame (carrier.rs:6) */
+    uint32_t n_tx_taps;          /* 0 => rectangular hold, the reference's TX (data.rs:66-79) */
+    const float* tx_taps;        /* else: FIR (fir.rs semantics) over the zero-stuffed symbol train */
+    uint32_t n_rx_taps;          /* the `lp` filter of Demodulator::new (demodulator.rs:20-30) */
+    const float* rx_taps;        /* e.g. modem_lowpass_taps() == src/bin/demodulate.rs:82-147 */
+    uint32_t decision_delay;     /* symbol k is sliced at sample k*sps + decision_delay */
+    float rx_gain;               /* 2.0 (demodulator.rs:53-54) */
+    float slicer_gain;           /* end-to-end gain g: slicer compares against g * const_iq */
+    uint32_t flags;              /* MODEM_FLAG_* */
+} modem_cfg_t;
+
+/* ------------------------------------------------------------------ host-side helpers
+ * Pure host code (no device needed): the constants a caller of the reference would get
+ * from Freq / Rates / the digital::* constructors, computed the reference's way (binary32,
+ * unfused, glibc sinf/cosf).
+ */
+float modem_sample_freq(size_t hz, size_t sr);                 /* freq.rs:19-26 */
+size_t modem_samples_per_symbol(size_t baud_rate, size_t sample_rate); /* rates.rs:12-18 */
+
+/* Constellation tables; each writes 2^bps (i,q) pairs to out_iq and returns bps (<0 on error). */
+int modem_const_bask(float amplitude, float* out_iq);                                  /* bask.rs */
+int modem_const_bpsk(float phase, float amplitude, float* out_iq);                     /* bpsk.rs */
+int modem_const_qpsk(float phase, float amplitude, float* out_iq);                     /* qpsk.rs */
+int modem_const_qam(uint32_t bps, float phase, float amplitude, float* out_iq);        /* qam.rs */
+int modem_const_mpsk(uint32_t bps, float phase_offset, float amplitude, float* out_iq);/* mpsk.rs */
+int modem_const_oqpsk(float amplitude, float* out_iq);                                 /* oqpsk.rs */
+int modem_const_dcqpsk(float amplitude, float* out_iq /* 2 tables: 8 pairs */);        /* dcqpsk.rs */
+typedef struct {
+    uint8_t start, end; /* Range<u8> */
+    float radius, phase;
+} modem_ring_t;                                                                        /* apsk.rs:60-67 */
+int modem_const_apsk(float amplitude, uint32_t bps, const modem_ring_t* rings, size_t n_rings,
+                     float* out_iq);                                                   /* apsk.rs */
+/* The memoryless `-m` names of src/bin/modulate.rs:74-95 with that file's constants
+ * (AMPLITUDE 1.0, bpsk phase pi/4, 16apsk rings, ...).  out_iq needs room for 512 pairs.
+ * Returns bps; *n_tables and *evenodd (1 => use q_offset = sps/2, modulate.rs:101-107) are set.
+ * Unknown or stateful (bfsk/mfsk/msk/cpfsk/dmpsk) names return MODEM_ERR_UNSUPPORTED. */
+int modem_const_by_name(const char* name, float* out_iq, uint32_t* n_tables, uint32_t* evenodd);
+
+const float* modem_lowpass_taps(size_t* n);  /* src/bin/demodulate.rs:82-147, 64 taps */
+/* root-raised-cosine, span*sps+1 taps, unit energy (extension) */
+int modem_rrc_taps(float* out, size_t span, size_t sps, double beta);
+/* AWGN sigma that gives the slicer the textbook Eb/N0 (DESIGN.md "AWGN scaling") */
+float modem_sigma_for_ebn0(const modem_cfg_t* cfg, double ebn0_db);
+
+/* ------------------------------------------------------------------ context */
+int modem_gpu_device_count(int* n);
+int modem_gpu_create(modem_ctx_t** ctx, int device, const modem_cfg_t* cfg);
+void modem_gpu_destroy(modem_ctx_t* ctx);
+/* Use the caller's CUDA stream (a cudaStream_t / CUstream handle) for all work of this ctx. */
+int modem_gpu_set_stream(modem_ctx_t* ctx, void* cuda_stream);
+/* Multi-carrier bank: frame f uses sample_freq[f / frames_per_channel] and
+ * phase_offset[...] (nullable => cfg.phase_offset).  n_channels == 0 restores cfg.sample_freq. */
+int modem_gpu_set_channels(modem_ctx_t* ctx, size_t n_channels, const float* sample_freq,
+                           const float* phase_offset, size_t frames_per_channel);
+int modem_gpu_synchronize(modem_ctx_t* ctx);
+
+size_t modem_gpu_frame_samples(const modem_ctx_t* ctx, size_t nbits);   /* floor(nbits/bps)*sps (data.rs:54-63) */
+size_t modem_gpu_decided_symbols(const modem_ctx_t* ctx, size_t L);     /* floor((L-1-delay-q_offset)/sps)+1 */
+
+/* ------------------------------------------------------------------ the path
+ * modulate: bits [F][nbits], one byte per bit (data.rs:35-40)  ->  tx [F][L] complex,
+ *   L = modem_gpu_frame_samples(nbits).  Replaces, per sample, Bits::next (data.rs:66-79),
+ *   DigitalPhasor::next (digital/phasor.rs:9-11), Carrier::next (carrier.rs:21-26) and
+ *   IQSample::modulate (modulator.rs:37-48) -- i.e. `DigitalModulator::new(..).map(|s| s.modulate())`.
+ *   iq (nullable): the baseband (i,q) pairs before mixing (IQSample.i/.q, modulate.rs:110-113).
+ */
+int modem_gpu_modulate(modem_ctx_t* ctx, const uint8_t* bits, size_t F, size_t nbits,
+                       modem_c32_t* tx, modem_c32_t* iq);
+
+/* awgn (extension): buf[f][n] += sigma * N(0,1) per component, Philox4x32-10 keyed by `seed`,
+ * counter = (n/2, global frame id frame0+f).  In place. */
+int modem_gpu_awgn(modem_ctx_t* ctx, modem_c32_t* buf, size_t F, size_t L, float sigma,
+                   uint64_t seed, uint64_t frame0);
+
+/* demodulate: rx [F][L] complex -> per frame K = modem_gpu_decided_symbols(L) decisions.
+ *   Replaces Demodulator::next (demodulator.rs:44-55) with its two FIRFilter::add
+ *   (fir.rs:18-34), plus the decimator/slicer extension.
+ *   sym  [F][K]      (nullable) symbol indices
+ *   bits [F][K*bps]  (nullable) demapped bits, one byte per bit, MSB first
+ *   soft [F][K]      (nullable) the filtered (I,Q) at the decision instants
+ *   filt [F][L]      (nullable) the full-rate filtered (I,Q) stream the reference emits
+ *                    (compute-bound parity/debug output)
+ *   sigma > 0 adds the same noise as modem_gpu_awgn(seed, frame0) while loading rx
+ *   (the buffer itself is not modified).
+ */
+int modem_gpu_demodulate(modem_ctx_t* ctx, const modem_c32_t* rx, size_t F, size_t L,
+                         uint8_t* sym, uint8_t* bits, modem_c32_t* soft, modem_c32_t* filt,
+                         float sigma, uint64_t seed, uint64_t frame0);
+
+/* demodulate_count: the stream-ordered, device-resident form used inside a loopback: like
+ * modem_gpu_demodulate (sym / bits nullable) but additionally compares every decided bit with
+ * ref_bits [F][ref_stride] (the bits that were modulated) and ACCUMULATES into the DEVICE
+ * counters[2] = {bit errors, bits compared}.  All pointers must be device pointers; nothing is
+ * synchronised, so the counters can feed modem_gpu_allreduce_counters on the same stream. */
+int modem_gpu_demodulate_count(modem_ctx_t* ctx, const modem_c32_t* rx, size_t F, size_t L,
+                               uint8_t* sym, uint8_t* bits, const uint8_t* ref_bits, size_t ref_stride,
+                               uint64_t* counters, float sigma, uint64_t seed, uint64_t frame0);
+
+/* loopback: modulate -> (AWGN) -> demodulate -> count bit errors against the input bits
+ * over the decided symbols.  tx (nullable => context scratch) receives the clean TX
+ * samples.  counters[0] += bit errors, counters[1] += bits compared (host pointer,
+ * read back after the work completes; this call synchronises). */
+int modem_gpu_loopback(modem_ctx_t* ctx, const uint8_t* bits, size_t F, size_t nbits,
+                       float sigma, uint64_t seed, uint64_t frame0, modem_c32_t* tx,
+                       uint8_t* sym, uint8_t* bits_out, uint64_t counters[2]);
+
+/* ------------------------------------------------------------------ memory helpers */
+int modem_gpu_malloc(modem_ctx_t* ctx, void** dptr, size_t bytes);
+int modem_gpu_free(modem_ctx_t* ctx, void* dptr);
+int modem_gpu_host_alloc(void** hptr, size_t bytes); /* pinned */
+int modem_gpu_host_free(void* hptr);
+int modem_gpu_memcpy_h2d(modem_ctx_t* ctx, void* dst, const void* src, size_t bytes);
+int modem_gpu_memcpy_d2h(modem_ctx_t* ctx, void* dst, const void* src, size_t bytes);
+
+/* ------------------------------------------------------------------ multi-GPU
+ * Frames (or channels) are sharded across ranks by the caller; the only exchange is one
+ * all-reduce of the error counters.  NCCL is loaded lazily (dlopen). */
+#define MODEM_COMM_ID_BYTES 128
+int modem_gpu_comm_unique_id(uint8_t id[MODEM_COMM_ID_BYTES]);
+int modem_gpu_comm_create(modem_comm_t** comm, modem_ctx_t* ctx, int n_ranks, int rank,
+                          const uint8_t id[MODEM_COMM_ID_BYTES]);
+int modem_gpu_allreduce_counters(modem_comm_t* comm, uint64_t* counters, size_t n);
+void modem_gpu_comm_destroy(modem_comm_t* comm);
+
+/* ------------------------------------------------------------------ diagnostics */
+const char* modem_gpu_strerror(int code);
+const char* modem_gpu_last_error(const modem_ctx_t* ctx); /* detail of the last failure */
+uint64_t modem_gpu_launch_count(const modem_ctx_t* ctx);  /* kernels launched by this ctx so far */
+int modem_gpu_abi_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MODEM_GPU_H */

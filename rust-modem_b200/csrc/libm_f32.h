@@ -108,18 +108,25 @@ MG_HD void mg_sincos_poly(double x, double x2, int neg, int n, float* sinp, floa
 }
 
 /* 4/pi as overlapping 32-bit words, for |y| >= 120 (Payne-Hanek style). */
-#if defined(__CUDA_ARCH__)
-__device__ __constant__ uint32_t mg_inv_pio4[24] = {
-#else
-static const uint32_t mg_inv_pio4[24] = {
+#define MG_INV_PIO4_INIT \
+    {0xa2,       0xa2f9,     0xa2f983,   0xa2f9836e, 0xf9836e4e, 0x836e4e44, 0x6e4e4415, 0x4e441529, \
+     0x441529fc, 0x1529fc27, 0x29fc2757, 0xfc2757d1, 0x2757d1f5, 0x57d1f534, 0xd1f534dd, 0xf534ddc0, \
+     0x34ddc0db, 0xddc0db62, 0xc0db6295, 0xdb629599, 0x6295993c, 0x95993c43, 0x993c4390, 0x3c439041}
+static const uint32_t mg_inv_pio4[24] = MG_INV_PIO4_INIT;
+#if defined(__CUDACC__)
+/* device copies live in global memory (L1-cached): the index differs per lane, which
+ * would serialise a __constant__ access */
+static __device__ const uint32_t mg_inv_pio4_dev[24] = MG_INV_PIO4_INIT;
 #endif
-    0xa2,       0xa2f9,     0xa2f983,   0xa2f9836e, 0xf9836e4e, 0x836e4e44, 0x6e4e4415, 0x4e441529,
-    0x441529fc, 0x1529fc27, 0x29fc2757, 0xfc2757d1, 0x2757d1f5, 0x57d1f534, 0xd1f534dd, 0xf534ddc0,
-    0x34ddc0db, 0xddc0db62, 0xc0db6295, 0xdb629599, 0x6295993c, 0x95993c43, 0x993c4390, 0x3c439041};
+#if defined(__CUDA_ARCH__)
+#define MG_INV_PIO4 mg_inv_pio4_dev
+#else
+#define MG_INV_PIO4 mg_inv_pio4
+#endif
 
 MG_HD double mg_reduce_large(uint32_t xi, int* np)
 {
-    const uint32_t* arr = &mg_inv_pio4[(xi >> 26) & 15];
+    const uint32_t* arr = &MG_INV_PIO4[(xi >> 26) & 15];
     int shift = (xi >> 23) & 7;
     uint64_t n, res0, res1, res2;
 
@@ -173,19 +180,24 @@ MG_HD void mg_sincosf(float y, float* sinp, float* cosp)
 }
 
 /* ---- logf ------------------------------------------------------------------ */
-#if defined(__CUDA_ARCH__)
-__device__ __constant__ double mg_logf_tab[16][2] = {
-#else
-static const double mg_logf_tab[16][2] = {
+#define MG_LOGF_TAB_INIT { \
+    {0x1.661ec79f8f3bep+0, -0x1.57bf7808caadep-2}, {0x1.571ed4aaf883dp+0, -0x1.2bef0a7c06ddbp-2}, \
+    {0x1.49539f0f010bp+0, -0x1.01eae7f513a67p-2},  {0x1.3c995b0b80385p+0, -0x1.b31d8a68224e9p-3}, \
+    {0x1.30d190c8864a5p+0, -0x1.6574f0ac07758p-3}, {0x1.25e227b0b8eap+0, -0x1.1aa2bc79c81p-3}, \
+    {0x1.1bb4a4a1a343fp+0, -0x1.a4e76ce8c0e5ep-4}, {0x1.12358f08ae5bap+0, -0x1.1973c5a611cccp-4}, \
+    {0x1.0953f419900a7p+0, -0x1.252f438e10c1ep-5}, {0x1p+0, 0x0p+0}, \
+    {0x1.e608cfd9a47acp-1, 0x1.aa5aa5df25984p-5},  {0x1.ca4b31f026aap-1, 0x1.c5e53aa362eb4p-4}, \
+    {0x1.b2036576afce6p-1, 0x1.526e57720db08p-3},  {0x1.9c2d163a1aa2dp-1, 0x1.bc2860d22477p-3}, \
+    {0x1.886e6037841edp-1, 0x1.1058bc8a07ee1p-2},  {0x1.767dcf5534862p-1, 0x1.4043057b6ee09p-2}}
+static const double mg_logf_tab[16][2] = MG_LOGF_TAB_INIT;
+#if defined(__CUDACC__)
+static __device__ const double mg_logf_tab_dev[16][2] = MG_LOGF_TAB_INIT;
 #endif
-    {0x1.661ec79f8f3bep+0, -0x1.57bf7808caadep-2}, {0x1.571ed4aaf883dp+0, -0x1.2bef0a7c06ddbp-2},
-    {0x1.49539f0f010bp+0, -0x1.01eae7f513a67p-2},  {0x1.3c995b0b80385p+0, -0x1.b31d8a68224e9p-3},
-    {0x1.30d190c8864a5p+0, -0x1.6574f0ac07758p-3}, {0x1.25e227b0b8eap+0, -0x1.1aa2bc79c81p-3},
-    {0x1.1bb4a4a1a343fp+0, -0x1.a4e76ce8c0e5ep-4}, {0x1.12358f08ae5bap+0, -0x1.1973c5a611cccp-4},
-    {0x1.0953f419900a7p+0, -0x1.252f438e10c1ep-5}, {0x1p+0, 0x0p+0},
-    {0x1.e608cfd9a47acp-1, 0x1.aa5aa5df25984p-5},  {0x1.ca4b31f026aap-1, 0x1.c5e53aa362eb4p-4},
-    {0x1.b2036576afce6p-1, 0x1.526e57720db08p-3},  {0x1.9c2d163a1aa2dp-1, 0x1.bc2860d22477p-3},
-    {0x1.886e6037841edp-1, 0x1.1058bc8a07ee1p-2},  {0x1.767dcf5534862p-1, 0x1.4043057b6ee09p-2}};
+#if defined(__CUDA_ARCH__)
+#define MG_LOGF_TAB mg_logf_tab_dev
+#else
+#define MG_LOGF_TAB mg_logf_tab
+#endif
 
 #define MG_LN2 0x1.62e42fefa39efp-1
 #define MG_LA0 (-0x1.00ea348b88334p-2)
@@ -206,8 +218,8 @@ MG_HD float mg_logf_pos(float x)
     int i = (int)((tmp >> 19) & 15u);
     int k = (int32_t)tmp >> 23;
     uint32_t iz = ix - (tmp & (0x1ffu << 23));
-    double invc = mg_logf_tab[i][0];
-    double logc = mg_logf_tab[i][1];
+    double invc = MG_LOGF_TAB[i][0];
+    double logc = MG_LOGF_TAB[i][1];
     double z = (double)MG_ASFLOAT(iz);
 
     double r = MG_DFMA(z, invc, -1.0);

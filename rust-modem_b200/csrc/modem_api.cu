@@ -1,0 +1,827 @@
+/*
+ * modem_api.cu -- the C ABI of include/modem_gpu.h: context, buffer staging, kernel
+ * selection and launch geometry.  No CPU fallback lives here: every compute entry needs
+ * a usable sm_100 device and fails with an error code otherwise.
+ */
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "../../include/modem_gpu.h"
+#include "kernels.cuh"
+
+using mg::u64;
+
+namespace {
+
+struct Scratch {
+    void* p = nullptr;
+    size_t cap = 0;
+};
+
+} // namespace
+
+struct modem_ctx {
+    int device = 0;
+    int sm_count = 148;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    modem_cfg_t cfg{};
+    std::vector<float> h_const, h_slut, h_tx_taps, h_rx_taps;
+    float2* d_lut = nullptr;
+    float2* d_slut = nullptr;
+    float* d_tx_taps = nullptr;
+    float* d_rx_taps = nullptr;
+    float* d_chan_w = nullptr;
+    float* d_chan_po = nullptr;
+    size_t n_channels = 0, frames_per_channel = 1;
+    u64* d_counters = nullptr;
+    Scratch s_bits, s_tx, s_iq, s_rx, s_sym, s_bits_out, s_soft, s_filt;
+    uint64_t launches = 0;
+    bool force_generic = false;
+    std::string last_error;
+};
+
+struct modem_comm {
+    void* nccl_comm = nullptr;
+    modem_ctx* ctx = nullptr;
+    u64* d_buf = nullptr;
+    size_t cap = 0;
+};
+
+namespace {
+
+thread_local std::string g_last_error;
+
+int fail(modem_ctx* ctx, int code, const std::string& msg)
+{
+    g_last_error = msg;
+    if (ctx) ctx->last_error = msg;
+    return code;
+}
+
+#define CK(ctx, call)                                                                                   \
+    do {                                                                                                \
+        cudaError_t e__ = (call);                                                                       \
+        if (e__ != cudaSuccess)                                                                         \
+            return fail((ctx), MODEM_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__));    \
+    } while (0)
+
+bool is_device_ptr(const void* p)
+{
+    if (!p) return false;
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged;
+}
+
+int ensure(modem_ctx* ctx, Scratch& s, size_t bytes)
+{
+    if (bytes <= s.cap) return MODEM_OK;
+    if (s.p) CK(ctx, cudaFree(s.p));
+    s.p = nullptr;
+    s.cap = 0;
+    cudaError_t e = cudaMalloc(&s.p, bytes);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return fail(ctx, MODEM_ERR_NOMEM, "cudaMalloc of " + std::to_string(bytes) + " bytes failed");
+    }
+    s.cap = bytes;
+    return MODEM_OK;
+}
+
+/* A buffer argument resolved to a device pointer: in place if the caller passed device
+ * memory, else staged through context scratch. */
+struct Staged {
+    void* dev = nullptr;
+    void* host = nullptr; /* non-null => copy back / from */
+    size_t bytes = 0;
+};
+
+int stage_in(modem_ctx* ctx, Scratch& s, const void* p, size_t bytes, Staged* out)
+{
+    out->bytes = bytes;
+    if (!p || bytes == 0) return MODEM_OK;
+    if (is_device_ptr(p)) {
+        out->dev = const_cast<void*>(p);
+        return MODEM_OK;
+    }
+    int rc = ensure(ctx, s, bytes);
+    if (rc) return rc;
+    CK(ctx, cudaMemcpyAsync(s.p, p, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    out->dev = s.p;
+    return MODEM_OK;
+}
+
+int stage_out(modem_ctx* ctx, Scratch& s, void* p, size_t bytes, Staged* out)
+{
+    out->bytes = bytes;
+    if (!p || bytes == 0) return MODEM_OK;
+    if (is_device_ptr(p)) {
+        out->dev = p;
+        return MODEM_OK;
+    }
+    int rc = ensure(ctx, s, bytes);
+    if (rc) return rc;
+    out->dev = s.p;
+    out->host = p;
+    return MODEM_OK;
+}
+
+int finish_out(modem_ctx* ctx, const Staged& st)
+{
+    if (st.host && st.bytes) CK(ctx, cudaMemcpyAsync(st.host, st.dev, st.bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    return MODEM_OK;
+}
+
+mg::ChannelView channel_view(const modem_ctx* ctx)
+{
+    mg::ChannelView v;
+    v.w = ctx->n_channels ? ctx->d_chan_w : nullptr;
+    v.po = ctx->n_channels ? ctx->d_chan_po : nullptr;
+    v.w0 = ctx->cfg.sample_freq;
+    v.po0 = ctx->cfg.phase_offset;
+    v.frames_per_channel = ctx->n_channels ? ctx->frames_per_channel : 1;
+    return v;
+}
+
+/* frames handled by one CTA: large enough to amortise the per-tile NCO table, small enough
+ * to leave several waves of CTAs; must divide frames_per_channel so a CTA sees one carrier. */
+uint32_t frames_per_block(const modem_ctx* ctx, u64 F, u64 tiles_x)
+{
+    const u64 target_ctas = (u64)ctx->sm_count * 16;
+    u64 fpb = (F * tiles_x) / std::max<u64>(target_ctas, 1);
+    fpb = std::min<u64>(std::max<u64>(fpb, 1), 32);
+    fpb = std::max<u64>(fpb, (F + 65534) / 65535); /* gridDim.y limit */
+    if (ctx->n_channels) {
+        u64 fc = ctx->frames_per_channel;
+        if (fpb > fc) fpb = fc;
+        while (fc % fpb) --fpb;
+    }
+    return (uint32_t)fpb;
+}
+
+template <int NT>
+mg::TapsParam<NT> taps_param(const std::vector<float>& h)
+{
+    mg::TapsParam<NT> t;
+    for (int i = 0; i < NT; ++i) t.h[i] = h[i];
+    return t;
+}
+
+bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+/* ------------------------------------------------------------------ TX launch */
+int launch_tx(modem_ctx* ctx, const uint8_t* d_bits, u64 F, u64 nbits, float2* d_tx, float2* d_iq)
+{
+    const modem_cfg_t& c = ctx->cfg;
+    mg::TxArgs a{};
+    a.bits = d_bits;
+    a.nbits = nbits;
+    a.tx = d_tx;
+    a.iq = d_iq;
+    a.nsym = nbits / c.bits_per_symbol;
+    a.L = a.nsym * c.samples_per_symbol;
+    a.F = F;
+    a.lut = ctx->d_lut;
+    a.bps = c.bits_per_symbol;
+    a.sps = c.samples_per_symbol;
+    a.n_tables = c.n_tables;
+    a.n_const = 1u << c.bits_per_symbol;
+    a.q_offset = c.q_offset;
+    a.ch = channel_view(ctx);
+    a.sample0 = c.sample0;
+    a.taps = ctx->d_tx_taps;
+    a.n_taps = c.n_tx_taps;
+    if (F == 0 || a.L == 0) return MODEM_OK;
+    if (a.nsym >= (1ull << 32)) return fail(ctx, MODEM_ERR_UNSUPPORTED, "more than 2^32 symbols per frame");
+    const bool fma = (c.flags & MODEM_FLAG_FUSED_MAC) != 0;
+    const bool vec_ok = (a.L % 2 == 0) && aligned16(d_tx) && aligned16(d_iq);
+
+    if (c.n_tx_taps == 0) {
+        const int vec = vec_ok ? 2 : 1;
+        const u64 tile = (u64)mg::kThreads * 2 * vec;
+        const u64 tiles = (a.L + tile - 1) / tile;
+        a.frames_per_block = frames_per_block(ctx, F, tiles);
+        dim3 grid((unsigned)tiles, (unsigned)((F + a.frames_per_block - 1) / a.frames_per_block));
+        if (vec == 2) mg::tx_rect_kernel<2><<<grid, mg::kThreads, 0, ctx->stream>>>(a);
+        else mg::tx_rect_kernel<1><<<grid, mg::kThreads, 0, ctx->stream>>>(a);
+    } else if (!ctx->force_generic && c.samples_per_symbol == 8 && c.n_tx_taps == 129 && c.q_offset == 0 && d_tx &&
+               !d_iq && vec_ok) {
+        const u64 tiles = (a.nsym + mg::kThreads - 1) / mg::kThreads;
+        a.frames_per_block = frames_per_block(ctx, F, tiles);
+        dim3 grid((unsigned)tiles, (unsigned)((F + a.frames_per_block - 1) / a.frames_per_block));
+        auto tp = taps_param<129>(ctx->h_tx_taps);
+        if (fma) mg::tx_shaped_fast_kernel<8, 129, true><<<grid, mg::kThreads, 0, ctx->stream>>>(a, tp);
+        else mg::tx_shaped_fast_kernel<8, 129, false><<<grid, mg::kThreads, 0, ctx->stream>>>(a, tp);
+    } else {
+        const uint32_t sps = c.samples_per_symbol, N = c.n_tx_taps;
+        uint32_t TS = std::max<uint32_t>(1, std::min<uint32_t>(256, 2048 / sps));
+        a.sym_tile = TS;
+        const uint32_t H = (N + sps - 1) / sps + 1;
+        const size_t smem = (size_t)TS * sps * sizeof(float2) + (size_t)N * 4 + 2 * (size_t)(TS + H) * 4;
+        if (smem > 200 * 1024) return fail(ctx, MODEM_ERR_UNSUPPORTED, "tx_taps too long for shared memory");
+        const u64 tiles = (a.nsym + TS - 1) / TS;
+        a.frames_per_block = frames_per_block(ctx, F, tiles);
+        dim3 grid((unsigned)tiles, (unsigned)((F + a.frames_per_block - 1) / a.frames_per_block));
+        if (fma) {
+            CK(ctx, cudaFuncSetAttribute(mg::tx_shaped_generic_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            mg::tx_shaped_generic_kernel<true><<<grid, mg::kThreads, smem, ctx->stream>>>(a);
+        } else {
+            CK(ctx, cudaFuncSetAttribute(mg::tx_shaped_generic_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            mg::tx_shaped_generic_kernel<false><<<grid, mg::kThreads, smem, ctx->stream>>>(a);
+        }
+    }
+    ctx->launches++;
+    CK(ctx, cudaGetLastError());
+    return MODEM_OK;
+}
+
+/* ------------------------------------------------------------------ RX launch */
+template <int NT>
+int launch_rx_fast(modem_ctx* ctx, mg::RxArgs& a, bool fma)
+{
+    using C = mg::RxFastCfg<8, NT>;
+    const u64 tiles = (a.K + C::TS - 1) / C::TS;
+    a.frames_per_block = frames_per_block(ctx, a.F, tiles);
+    dim3 grid((unsigned)tiles, (unsigned)((a.F + a.frames_per_block - 1) / a.frames_per_block));
+    auto tp = taps_param<NT>(ctx->h_rx_taps);
+    if (fma) {
+        CK(ctx, cudaFuncSetAttribute(mg::rx_fast_kernel<8, NT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
+        mg::rx_fast_kernel<8, NT, true><<<grid, mg::kThreads, C::SMEM, ctx->stream>>>(a, tp);
+    } else {
+        CK(ctx, cudaFuncSetAttribute(mg::rx_fast_kernel<8, NT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
+        mg::rx_fast_kernel<8, NT, false><<<grid, mg::kThreads, C::SMEM, ctx->stream>>>(a, tp);
+    }
+    return MODEM_OK;
+}
+
+int launch_rx(modem_ctx* ctx, const float2* d_rx, u64 F, u64 L, uint8_t* d_sym, uint8_t* d_bits, float2* d_soft,
+              float2* d_filt, const uint8_t* d_ref, u64 ref_stride, u64* d_counters, float sigma, uint64_t seed,
+              uint64_t frame0)
+{
+    const modem_cfg_t& c = ctx->cfg;
+    mg::RxArgs a{};
+    a.rx = d_rx;
+    a.L = L;
+    a.F = F;
+    a.K = modem_gpu_decided_symbols(ctx, L);
+    a.sym = d_sym;
+    a.bits = d_bits;
+    a.soft = d_soft;
+    a.filt = d_filt;
+    a.ref_bits = d_ref;
+    a.ref_stride = ref_stride;
+    a.counters = d_counters;
+    a.slut = ctx->d_slut;
+    a.bps = c.bits_per_symbol;
+    a.sps = c.samples_per_symbol;
+    a.n_tables = c.n_tables;
+    a.n_const = 1u << c.bits_per_symbol;
+    a.q_offset = c.q_offset;
+    a.delay = c.decision_delay;
+    a.rx_gain = c.rx_gain;
+    a.ch = channel_view(ctx);
+    a.sample0 = c.sample0;
+    a.taps = ctx->d_rx_taps;
+    a.n_taps = c.n_rx_taps;
+    a.nz.sigma = sigma;
+    a.nz.seed = seed;
+    a.nz.frame0 = frame0;
+    if (F == 0 || L == 0) return MODEM_OK;
+    const bool fma = (c.flags & MODEM_FLAG_FUSED_MAC) != 0;
+    const uint32_t N = c.n_rx_taps, sps = c.samples_per_symbol;
+
+    if (d_filt) {
+        const uint32_t TILE = mg::kThreads * 4;
+        const size_t smem = (size_t)(TILE + N - 1) * 8 + (size_t)N * 4;
+        if (smem > 200 * 1024) return fail(ctx, MODEM_ERR_UNSUPPORTED, "rx_taps too long for shared memory");
+        dim3 grid((unsigned)((L + TILE - 1) / TILE), (unsigned)F);
+        if (F > 65535) return fail(ctx, MODEM_ERR_UNSUPPORTED, "full-rate dump limited to 65535 frames per call");
+        if (fma) {
+            CK(ctx, cudaFuncSetAttribute(mg::rx_fullrate_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            mg::rx_fullrate_kernel<true><<<grid, mg::kThreads, smem, ctx->stream>>>(a);
+        } else {
+            CK(ctx, cudaFuncSetAttribute(mg::rx_fullrate_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            mg::rx_fullrate_kernel<false><<<grid, mg::kThreads, smem, ctx->stream>>>(a);
+        }
+        ctx->launches++;
+        CK(ctx, cudaGetLastError());
+    }
+    if (a.K == 0 || !(d_sym || d_bits || d_soft || d_ref)) return MODEM_OK;
+
+    const bool fast_ok = !ctx->force_generic && sps == 8 && c.q_offset == 0 && (L % 2 == 0) && aligned16(d_rx);
+    if (fast_ok && N == 64) {
+        int rc = launch_rx_fast<64>(ctx, a, fma);
+        if (rc) return rc;
+    } else if (fast_ok && N == 129) {
+        int rc = launch_rx_fast<129>(ctx, a, fma);
+        if (rc) return rc;
+    } else {
+        const size_t budget = 96 * 1024;
+        if ((size_t)N * 4 + (size_t)(N + c.q_offset) * 16 > budget)
+            return fail(ctx, MODEM_ERR_UNSUPPORTED, "rx_taps too long for shared memory");
+        const size_t rmax = (budget - (size_t)N * 4) / 16;
+        uint32_t TS = (uint32_t)std::min<size_t>(256, (rmax - N - c.q_offset) / sps + 1);
+        TS = std::max<uint32_t>(TS, 1);
+        a.sym_tile = TS;
+        const size_t R = (size_t)(TS - 1) * sps + N + c.q_offset;
+        const size_t smem = R * 16 + (size_t)N * 4;
+        const u64 tiles = (a.K + TS - 1) / TS;
+        a.frames_per_block = frames_per_block(ctx, F, tiles);
+        dim3 grid((unsigned)tiles, (unsigned)((F + a.frames_per_block - 1) / a.frames_per_block));
+        if (fma) {
+            CK(ctx, cudaFuncSetAttribute(mg::rx_generic_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            mg::rx_generic_kernel<true><<<grid, mg::kThreads, smem, ctx->stream>>>(a);
+        } else {
+            CK(ctx, cudaFuncSetAttribute(mg::rx_generic_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            mg::rx_generic_kernel<false><<<grid, mg::kThreads, smem, ctx->stream>>>(a);
+        }
+    }
+    ctx->launches++;
+    CK(ctx, cudaGetLastError());
+    return MODEM_OK;
+}
+
+int upload(modem_ctx* ctx, void** dptr, const void* src, size_t bytes)
+{
+    if (*dptr) {
+        CK(ctx, cudaFree(*dptr));
+        *dptr = nullptr;
+    }
+    if (!bytes) return MODEM_OK;
+    cudaError_t e = cudaMalloc(dptr, bytes);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return fail(ctx, MODEM_ERR_NOMEM, "cudaMalloc failed");
+    }
+    CK(ctx, cudaMemcpy(*dptr, src, bytes, cudaMemcpyHostToDevice));
+    return MODEM_OK;
+}
+
+} // namespace
+
+extern "C" {
+
+int modem_gpu_abi_version(void) { return MODEM_GPU_ABI_VERSION; }
+
+const char* modem_gpu_strerror(int code)
+{
+    switch (code) {
+    case MODEM_OK: return "ok";
+    case MODEM_ERR_INVALID: return "invalid argument or configuration";
+    case MODEM_ERR_CUDA: return "CUDA runtime error";
+    case MODEM_ERR_NOMEM: return "out of device memory";
+    case MODEM_ERR_UNSUPPORTED: return "unsupported configuration";
+    case MODEM_ERR_NCCL: return "NCCL error";
+    case MODEM_ERR_NO_DEVICE: return "no usable sm_100 CUDA device (this library has no CPU fallback)";
+    default: return "unknown error";
+    }
+}
+
+const char* modem_gpu_last_error(const modem_ctx_t* ctx) { return ctx ? ctx->last_error.c_str() : g_last_error.c_str(); }
+
+uint64_t modem_gpu_launch_count(const modem_ctx_t* ctx) { return ctx ? ctx->launches : 0; }
+
+int modem_gpu_device_count(int* n)
+{
+    if (!n) return MODEM_ERR_INVALID;
+    int c = 0;
+    cudaError_t e = cudaGetDeviceCount(&c);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        *n = 0;
+        return fail(nullptr, MODEM_ERR_NO_DEVICE, std::string("cudaGetDeviceCount: ") + cudaGetErrorString(e));
+    }
+    *n = c;
+    return MODEM_OK;
+}
+
+int modem_gpu_create(modem_ctx_t** out, int device, const modem_cfg_t* cfg)
+{
+    if (!out || !cfg) return fail(nullptr, MODEM_ERR_INVALID, "null argument");
+    *out = nullptr;
+    if (cfg->struct_size != sizeof(modem_cfg_t)) return fail(nullptr, MODEM_ERR_INVALID, "modem_cfg_t size mismatch (ABI)");
+    if (cfg->bits_per_symbol < 1 || cfg->bits_per_symbol > 8) return fail(nullptr, MODEM_ERR_INVALID, "bits_per_symbol must be 1..8");
+    if (cfg->samples_per_symbol < 1) return fail(nullptr, MODEM_ERR_INVALID, "samples_per_symbol must be >= 1");
+    if (cfg->n_tables < 1 || (cfg->n_tables << cfg->bits_per_symbol) > (uint32_t)mg::kMaxLut || !cfg->const_iq)
+        return fail(nullptr, MODEM_ERR_INVALID, "bad constellation table");
+    if (cfg->n_rx_taps < 1 || !cfg->rx_taps) return fail(nullptr, MODEM_ERR_INVALID, "rx_taps required");
+    if (cfg->n_tx_taps && !cfg->tx_taps) return fail(nullptr, MODEM_ERR_INVALID, "tx_taps missing");
+    if (cfg->q_offset && (cfg->bits_per_symbol != 2 || cfg->q_offset >= cfg->samples_per_symbol))
+        return fail(nullptr, MODEM_ERR_INVALID, "q_offset needs bits_per_symbol == 2 and q_offset < sps (data.rs:91-92)");
+
+    int ndev = 0;
+    int rc = modem_gpu_device_count(&ndev);
+    if (rc) return rc;
+    if (device < 0 || device >= ndev) return fail(nullptr, MODEM_ERR_NO_DEVICE, "no such CUDA device");
+    cudaDeviceProp prop;
+    CK(nullptr, cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10)
+        return fail(nullptr, MODEM_ERR_NO_DEVICE,
+                    std::string("device is sm_") + std::to_string(prop.major) + std::to_string(prop.minor) + ", kernels are built for sm_100a only");
+    CK(nullptr, cudaSetDevice(device));
+
+    modem_ctx* ctx = new modem_ctx();
+    ctx->device = device;
+    ctx->sm_count = prop.multiProcessorCount;
+    ctx->cfg = *cfg;
+    const size_t np = (size_t)cfg->n_tables << cfg->bits_per_symbol;
+    ctx->h_const.assign(cfg->const_iq, cfg->const_iq + 2 * np);
+    ctx->h_slut.resize(2 * np);
+    for (size_t i = 0; i < 2 * np; ++i) {
+        volatile float v = cfg->slicer_gain * ctx->h_const[i]; /* one rounded binary32 product, as the oracle's g * c */
+        ctx->h_slut[i] = v;
+    }
+    ctx->h_rx_taps.assign(cfg->rx_taps, cfg->rx_taps + cfg->n_rx_taps);
+    if (cfg->n_tx_taps) ctx->h_tx_taps.assign(cfg->tx_taps, cfg->tx_taps + cfg->n_tx_taps);
+    ctx->cfg.const_iq = ctx->h_const.data();
+    ctx->cfg.rx_taps = ctx->h_rx_taps.data();
+    ctx->cfg.tx_taps = cfg->n_tx_taps ? ctx->h_tx_taps.data() : nullptr;
+    const char* fg = getenv("MODEM_GPU_FORCE_GENERIC");
+    ctx->force_generic = fg && fg[0] == '1';
+
+    rc = MODEM_OK;
+    cudaError_t e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) rc = fail(nullptr, MODEM_ERR_CUDA, std::string("cudaStreamCreate: ") + cudaGetErrorString(e));
+    ctx->own_stream = rc == MODEM_OK;
+    if (!rc) rc = upload(ctx, (void**)&ctx->d_lut, ctx->h_const.data(), ctx->h_const.size() * 4);
+    if (!rc) rc = upload(ctx, (void**)&ctx->d_slut, ctx->h_slut.data(), ctx->h_slut.size() * 4);
+    if (!rc) rc = upload(ctx, (void**)&ctx->d_rx_taps, ctx->h_rx_taps.data(), ctx->h_rx_taps.size() * 4);
+    if (!rc && cfg->n_tx_taps) rc = upload(ctx, (void**)&ctx->d_tx_taps, ctx->h_tx_taps.data(), ctx->h_tx_taps.size() * 4);
+    if (!rc) {
+        e = cudaMalloc((void**)&ctx->d_counters, 2 * sizeof(u64));
+        if (e != cudaSuccess) rc = fail(nullptr, MODEM_ERR_NOMEM, "cudaMalloc counters");
+    }
+    if (rc) {
+        std::string msg = g_last_error;
+        modem_gpu_destroy(ctx);
+        g_last_error = msg;
+        return rc;
+    }
+    *out = ctx;
+    return MODEM_OK;
+}
+
+void modem_gpu_destroy(modem_ctx_t* ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    void* ptrs[] = {ctx->d_lut, ctx->d_slut, ctx->d_tx_taps, ctx->d_rx_taps, ctx->d_chan_w, ctx->d_chan_po, ctx->d_counters,
+                    ctx->s_bits.p, ctx->s_tx.p, ctx->s_iq.p, ctx->s_rx.p, ctx->s_sym.p, ctx->s_bits_out.p, ctx->s_soft.p, ctx->s_filt.p};
+    for (void* p : ptrs)
+        if (p) cudaFree(p);
+    if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+    cudaGetLastError();
+    delete ctx;
+}
+
+int modem_gpu_set_stream(modem_ctx_t* ctx, void* cuda_stream)
+{
+    if (!ctx) return MODEM_ERR_INVALID;
+    CK(ctx, cudaSetDevice(ctx->device));
+    if (ctx->own_stream && ctx->stream) {
+        CK(ctx, cudaStreamSynchronize(ctx->stream));
+        CK(ctx, cudaStreamDestroy(ctx->stream));
+    }
+    ctx->stream = static_cast<cudaStream_t>(cuda_stream);
+    ctx->own_stream = false;
+    return MODEM_OK;
+}
+
+int modem_gpu_set_channels(modem_ctx_t* ctx, size_t n_channels, const float* sample_freq, const float* phase_offset,
+                           size_t frames_per_channel)
+{
+    if (!ctx) return MODEM_ERR_INVALID;
+    CK(ctx, cudaSetDevice(ctx->device));
+    CK(ctx, cudaStreamSynchronize(ctx->stream));
+    if (n_channels == 0) {
+        ctx->n_channels = 0;
+        ctx->frames_per_channel = 1;
+        return MODEM_OK;
+    }
+    if (!sample_freq || frames_per_channel == 0) return fail(ctx, MODEM_ERR_INVALID, "set_channels: bad arguments");
+    std::vector<float> po(n_channels, ctx->cfg.phase_offset);
+    if (phase_offset) po.assign(phase_offset, phase_offset + n_channels);
+    int rc = upload(ctx, (void**)&ctx->d_chan_w, sample_freq, n_channels * 4);
+    if (!rc) rc = upload(ctx, (void**)&ctx->d_chan_po, po.data(), n_channels * 4);
+    if (rc) return rc;
+    ctx->n_channels = n_channels;
+    ctx->frames_per_channel = frames_per_channel;
+    return MODEM_OK;
+}
+
+int modem_gpu_synchronize(modem_ctx_t* ctx)
+{
+    if (!ctx) return MODEM_ERR_INVALID;
+    CK(ctx, cudaStreamSynchronize(ctx->stream));
+    return MODEM_OK;
+}
+
+size_t modem_gpu_frame_samples(const modem_ctx_t* ctx, size_t nbits)
+{
+    if (!ctx) return 0;
+    return (nbits / ctx->cfg.bits_per_symbol) * ctx->cfg.samples_per_symbol;
+}
+
+size_t modem_gpu_decided_symbols(const modem_ctx_t* ctx, size_t L)
+{
+    if (!ctx) return 0;
+    const size_t last = (size_t)ctx->cfg.decision_delay + ctx->cfg.q_offset;
+    if (L <= last) return 0;
+    return (L - 1 - last) / ctx->cfg.samples_per_symbol + 1;
+}
+
+int modem_gpu_modulate(modem_ctx_t* ctx, const uint8_t* bits, size_t F, size_t nbits, modem_c32_t* tx, modem_c32_t* iq)
+{
+    if (!ctx || (!bits && F && nbits) || (!tx && !iq)) return fail(ctx, MODEM_ERR_INVALID, "modulate: null argument");
+    CK(ctx, cudaSetDevice(ctx->device));
+    if (ctx->n_channels && F > ctx->n_channels * ctx->frames_per_channel)
+        return fail(ctx, MODEM_ERR_INVALID, "modulate: more frames than channels * frames_per_channel");
+    const size_t L = modem_gpu_frame_samples(ctx, nbits);
+    Staged sb, st, si;
+    int rc = stage_in(ctx, ctx->s_bits, bits, F * nbits, &sb);
+    if (!rc) rc = stage_out(ctx, ctx->s_tx, tx, F * L * sizeof(float2), &st);
+    if (!rc) rc = stage_out(ctx, ctx->s_iq, iq, F * L * sizeof(float2), &si);
+    if (!rc) rc = launch_tx(ctx, (const uint8_t*)sb.dev, F, nbits, (float2*)st.dev, (float2*)si.dev);
+    if (!rc) rc = finish_out(ctx, st);
+    if (!rc) rc = finish_out(ctx, si);
+    if (!rc && (st.host || si.host)) CK(ctx, cudaStreamSynchronize(ctx->stream));
+    return rc;
+}
+
+int modem_gpu_awgn(modem_ctx_t* ctx, modem_c32_t* buf, size_t F, size_t L, float sigma, uint64_t seed, uint64_t frame0)
+{
+    if (!ctx || (!buf && F && L)) return fail(ctx, MODEM_ERR_INVALID, "awgn: null argument");
+    CK(ctx, cudaSetDevice(ctx->device));
+    if (F == 0 || L == 0) return MODEM_OK;
+    const size_t bytes = F * L * sizeof(float2);
+    float2* d = (float2*)buf;
+    const bool host = !is_device_ptr(buf);
+    if (host) {
+        int rc = ensure(ctx, ctx->s_rx, bytes);
+        if (rc) return rc;
+        d = (float2*)ctx->s_rx.p;
+        CK(ctx, cudaMemcpyAsync(d, buf, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    mg::Noise nz{sigma, seed, frame0};
+    const u64 pairs = (u64)F * ((L + 1) / 2);
+    const unsigned blocks = (unsigned)std::min<u64>((pairs + mg::kThreads - 1) / mg::kThreads, (u64)ctx->sm_count * 32);
+    mg::awgn_kernel<<<blocks, mg::kThreads, 0, ctx->stream>>>(d, F, L, nz);
+    ctx->launches++;
+    CK(ctx, cudaGetLastError());
+    if (host) {
+        CK(ctx, cudaMemcpyAsync(buf, d, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    return MODEM_OK;
+}
+
+int modem_gpu_demodulate(modem_ctx_t* ctx, const modem_c32_t* rx, size_t F, size_t L, uint8_t* sym, uint8_t* bits,
+                         modem_c32_t* soft, modem_c32_t* filt, float sigma, uint64_t seed, uint64_t frame0)
+{
+    if (!ctx || (!rx && F && L)) return fail(ctx, MODEM_ERR_INVALID, "demodulate: null argument");
+    CK(ctx, cudaSetDevice(ctx->device));
+    if (ctx->n_channels && F > ctx->n_channels * ctx->frames_per_channel)
+        return fail(ctx, MODEM_ERR_INVALID, "demodulate: more frames than channels * frames_per_channel");
+    const size_t K = modem_gpu_decided_symbols(ctx, L);
+    const size_t bps = ctx->cfg.bits_per_symbol;
+    Staged sr, ss, sb, so, sf;
+    int rc = stage_in(ctx, ctx->s_rx, rx, F * L * sizeof(float2), &sr);
+    if (!rc) rc = stage_out(ctx, ctx->s_sym, sym, F * K, &ss);
+    if (!rc) rc = stage_out(ctx, ctx->s_bits_out, bits, F * K * bps, &sb);
+    if (!rc) rc = stage_out(ctx, ctx->s_soft, soft, F * K * sizeof(float2), &so);
+    if (!rc) rc = stage_out(ctx, ctx->s_filt, filt, F * L * sizeof(float2), &sf);
+    if (!rc)
+        rc = launch_rx(ctx, (const float2*)sr.dev, F, L, (uint8_t*)ss.dev, (uint8_t*)sb.dev, (float2*)so.dev, (float2*)sf.dev,
+                       nullptr, 0, nullptr, sigma, seed, frame0);
+    if (!rc) rc = finish_out(ctx, ss);
+    if (!rc) rc = finish_out(ctx, sb);
+    if (!rc) rc = finish_out(ctx, so);
+    if (!rc) rc = finish_out(ctx, sf);
+    if (!rc && (ss.host || sb.host || so.host || sf.host)) CK(ctx, cudaStreamSynchronize(ctx->stream));
+    return rc;
+}
+
+int modem_gpu_demodulate_count(modem_ctx_t* ctx, const modem_c32_t* rx, size_t F, size_t L, uint8_t* sym, uint8_t* bits,
+                               const uint8_t* ref_bits, size_t ref_stride, uint64_t* counters, float sigma, uint64_t seed,
+                               uint64_t frame0)
+{
+    if (!ctx || !rx || !ref_bits || !counters) return fail(ctx, MODEM_ERR_INVALID, "demodulate_count: null argument");
+    CK(ctx, cudaSetDevice(ctx->device));
+    if (!is_device_ptr(rx) || !is_device_ptr(ref_bits) || !is_device_ptr(counters) || (sym && !is_device_ptr(sym)) ||
+        (bits && !is_device_ptr(bits)))
+        return fail(ctx, MODEM_ERR_INVALID, "demodulate_count: device pointers required");
+    if (ctx->n_channels && F > ctx->n_channels * ctx->frames_per_channel)
+        return fail(ctx, MODEM_ERR_INVALID, "demodulate_count: more frames than channels * frames_per_channel");
+    if (ref_stride < modem_gpu_decided_symbols(ctx, L) * ctx->cfg.bits_per_symbol)
+        return fail(ctx, MODEM_ERR_INVALID, "demodulate_count: ref_stride shorter than the decided bits");
+    return launch_rx(ctx, (const float2*)rx, F, L, sym, bits, nullptr, nullptr, ref_bits, ref_stride, (u64*)counters, sigma,
+                     seed, frame0);
+}
+
+int modem_gpu_loopback(modem_ctx_t* ctx, const uint8_t* bits, size_t F, size_t nbits, float sigma, uint64_t seed,
+                       uint64_t frame0, modem_c32_t* tx, uint8_t* sym, uint8_t* bits_out, uint64_t counters[2])
+{
+    if (!ctx || (!bits && F && nbits)) return fail(ctx, MODEM_ERR_INVALID, "loopback: null argument");
+    CK(ctx, cudaSetDevice(ctx->device));
+    if (ctx->n_channels && F > ctx->n_channels * ctx->frames_per_channel)
+        return fail(ctx, MODEM_ERR_INVALID, "loopback: more frames than channels * frames_per_channel");
+    const size_t L = modem_gpu_frame_samples(ctx, nbits);
+    const size_t K = modem_gpu_decided_symbols(ctx, L);
+    const size_t bps = ctx->cfg.bits_per_symbol;
+    Staged sb, st, ss, so;
+    int rc = stage_in(ctx, ctx->s_bits, bits, F * nbits, &sb);
+    if (rc) return rc;
+    if (tx) {
+        rc = stage_out(ctx, ctx->s_tx, tx, F * L * sizeof(float2), &st);
+    } else {
+        rc = ensure(ctx, ctx->s_tx, F * L * sizeof(float2));
+        st.dev = ctx->s_tx.p;
+    }
+    if (!rc) rc = stage_out(ctx, ctx->s_sym, sym, F * K, &ss);
+    if (!rc) rc = stage_out(ctx, ctx->s_bits_out, bits_out, F * K * bps, &so);
+    if (rc) return rc;
+    CK(ctx, cudaMemsetAsync(ctx->d_counters, 0, 2 * sizeof(u64), ctx->stream));
+    rc = launch_tx(ctx, (const uint8_t*)sb.dev, F, nbits, (float2*)st.dev, nullptr);
+    if (!rc)
+        rc = launch_rx(ctx, (const float2*)st.dev, F, L, (uint8_t*)ss.dev, (uint8_t*)so.dev, nullptr, nullptr,
+                       (const uint8_t*)sb.dev, nbits, ctx->d_counters, sigma, seed, frame0);
+    if (!rc) rc = finish_out(ctx, st);
+    if (!rc) rc = finish_out(ctx, ss);
+    if (!rc) rc = finish_out(ctx, so);
+    if (rc) return rc;
+    u64 h[2] = {0, 0};
+    CK(ctx, cudaMemcpyAsync(h, ctx->d_counters, sizeof h, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(ctx, cudaStreamSynchronize(ctx->stream));
+    if (counters) {
+        counters[0] += h[0];
+        counters[1] += h[1];
+    }
+    return MODEM_OK;
+}
+
+/* ------------------------------------------------------------------ memory helpers */
+int modem_gpu_malloc(modem_ctx_t* ctx, void** dptr, size_t bytes)
+{
+    if (!ctx || !dptr) return MODEM_ERR_INVALID;
+    CK(ctx, cudaSetDevice(ctx->device));
+    cudaError_t e = cudaMalloc(dptr, bytes ? bytes : 1);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return fail(ctx, MODEM_ERR_NOMEM, "cudaMalloc failed");
+    }
+    return MODEM_OK;
+}
+int modem_gpu_free(modem_ctx_t* ctx, void* dptr)
+{
+    if (!ctx) return MODEM_ERR_INVALID;
+    CK(ctx, cudaSetDevice(ctx->device));
+    CK(ctx, cudaFree(dptr));
+    return MODEM_OK;
+}
+int modem_gpu_host_alloc(void** hptr, size_t bytes)
+{
+    if (!hptr) return MODEM_ERR_INVALID;
+    cudaError_t e = cudaMallocHost(hptr, bytes ? bytes : 1);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return fail(nullptr, MODEM_ERR_NOMEM, std::string("cudaMallocHost: ") + cudaGetErrorString(e));
+    }
+    return MODEM_OK;
+}
+int modem_gpu_host_free(void* hptr)
+{
+    CK(nullptr, cudaFreeHost(hptr));
+    return MODEM_OK;
+}
+int modem_gpu_memcpy_h2d(modem_ctx_t* ctx, void* dst, const void* src, size_t bytes)
+{
+    if (!ctx) return MODEM_ERR_INVALID;
+    CK(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    CK(ctx, cudaStreamSynchronize(ctx->stream));
+    return MODEM_OK;
+}
+int modem_gpu_memcpy_d2h(modem_ctx_t* ctx, void* dst, const void* src, size_t bytes)
+{
+    if (!ctx) return MODEM_ERR_INVALID;
+    CK(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(ctx, cudaStreamSynchronize(ctx->stream));
+    return MODEM_OK;
+}
+
+/* ------------------------------------------------------------------ NCCL (lazy) */
+struct Id128 { /* ncclUniqueId */
+    char internal[MODEM_COMM_ID_BYTES];
+};
+namespace {
+struct NcclApi {
+    void* h = nullptr;
+    int (*GetUniqueId)(void*) = nullptr;
+    int (*CommInitRank)(void**, int, Id128 /* by value */, int) = nullptr;
+    int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+    int (*CommDestroy)(void*) = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+};
+NcclApi g_nccl;
+int nccl_load()
+{
+    if (g_nccl.h) return MODEM_OK;
+    const char* names[] = {"libnccl.so.2", "libnccl.so"};
+    for (const char* n : names) {
+        g_nccl.h = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+        if (g_nccl.h) break;
+    }
+    if (!g_nccl.h) return fail(nullptr, MODEM_ERR_NCCL, std::string("dlopen libnccl.so.2: ") + dlerror());
+    g_nccl.GetUniqueId = (int (*)(void*))dlsym(g_nccl.h, "ncclGetUniqueId");
+    g_nccl.CommInitRank = (int (*)(void**, int, Id128, int))dlsym(g_nccl.h, "ncclCommInitRank");
+    g_nccl.AllReduce = (int (*)(const void*, void*, size_t, int, int, void*, cudaStream_t))dlsym(g_nccl.h, "ncclAllReduce");
+    g_nccl.CommDestroy = (int (*)(void*))dlsym(g_nccl.h, "ncclCommDestroy");
+    g_nccl.GetErrorString = (const char* (*)(int))dlsym(g_nccl.h, "ncclGetErrorString");
+    if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllReduce || !g_nccl.CommDestroy)
+        return fail(nullptr, MODEM_ERR_NCCL, "libnccl is missing required symbols");
+    return MODEM_OK;
+}
+int nccl_fail(modem_ctx* ctx, const char* what, int r)
+{
+    return fail(ctx, MODEM_ERR_NCCL, std::string(what) + ": " + (g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "error"));
+}
+} // namespace
+
+int modem_gpu_comm_unique_id(uint8_t id[MODEM_COMM_ID_BYTES])
+{
+    if (!id) return MODEM_ERR_INVALID;
+    int rc = nccl_load();
+    if (rc) return rc;
+    Id128 u;
+    memset(&u, 0, sizeof u);
+    int r = g_nccl.GetUniqueId(&u);
+    if (r) return nccl_fail(nullptr, "ncclGetUniqueId", r);
+    memcpy(id, &u, sizeof u);
+    return MODEM_OK;
+}
+
+int modem_gpu_comm_create(modem_comm_t** out, modem_ctx_t* ctx, int n_ranks, int rank, const uint8_t id[MODEM_COMM_ID_BYTES])
+{
+    if (!out || !ctx || !id || n_ranks < 1 || rank < 0 || rank >= n_ranks) return fail(ctx, MODEM_ERR_INVALID, "comm_create: bad arguments");
+    int rc = nccl_load();
+    if (rc) return rc;
+    CK(ctx, cudaSetDevice(ctx->device));
+    modem_comm* c = new modem_comm();
+    c->ctx = ctx;
+    Id128 u;
+    memcpy(&u, id, sizeof u);
+    int r = g_nccl.CommInitRank(&c->nccl_comm, n_ranks, u, rank);
+    if (r) {
+        delete c;
+        return nccl_fail(ctx, "ncclCommInitRank", r);
+    }
+    *out = c;
+    return MODEM_OK;
+}
+
+int modem_gpu_allreduce_counters(modem_comm_t* comm, uint64_t* counters, size_t n)
+{
+    if (!comm || !counters || n == 0) return MODEM_ERR_INVALID;
+    modem_ctx* ctx = comm->ctx;
+    CK(ctx, cudaSetDevice(ctx->device));
+    const bool dev = is_device_ptr(counters);
+    u64* d = (u64*)counters;
+    if (!dev) {
+        if (comm->cap < n) {
+            if (comm->d_buf) CK(ctx, cudaFree(comm->d_buf));
+            CK(ctx, cudaMalloc((void**)&comm->d_buf, n * sizeof(u64)));
+            comm->cap = n;
+        }
+        d = comm->d_buf;
+        CK(ctx, cudaMemcpyAsync(d, counters, n * sizeof(u64), cudaMemcpyHostToDevice, ctx->stream));
+    }
+    /* the single collective of the path: ncclUint64 = 5, ncclSum = 0 */
+    int r = g_nccl.AllReduce(d, d, n, 5, 0, comm->nccl_comm, ctx->stream);
+    if (r) return nccl_fail(ctx, "ncclAllReduce", r);
+    if (!dev) {
+        CK(ctx, cudaMemcpyAsync(counters, d, n * sizeof(u64), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    return MODEM_OK;
+}
+
+void modem_gpu_comm_destroy(modem_comm_t* comm)
+{
+    if (!comm) return;
+    if (comm->nccl_comm && g_nccl.CommDestroy) g_nccl.CommDestroy(comm->nccl_comm);
+    if (comm->d_buf) cudaFree(comm->d_buf);
+    delete comm;
+}
+
+} /* extern "C" */

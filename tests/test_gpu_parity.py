@@ -1,0 +1,318 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle on the same
+seeded inputs.
+
+Bar (BASELINE.json north_star): demodulated bits and symbol indices bit-exact; TX and
+filtered sample buffers within max error <= 1e-5 (relative to the buffer's peak -- the
+per-sample relative error is unbounded at carrier zero crossings).  The design goes further
+(device libm == glibc, unfused binary32 ops in reference order), so in the default mode the
+buffers are also expected to be BIT-identical; `assert_buffers` checks both and reports them
+separately.
+"""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import MEMORYLESS, path_kwargs
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-5
+
+
+def assert_buffers(got, ref, what, exact=True):
+    assert got.shape == ref.shape, (what, got.shape, ref.shape)
+    peak = float(np.abs(ref).max()) if ref.size else 1.0
+    err = float(np.abs(got.astype(np.float64) - ref.astype(np.float64)).max()) / (peak or 1.0) if ref.size else 0.0
+    assert err <= TOL, f"{what}: max error {err:.3g} of peak exceeds {TOL}"
+    if exact:
+        nbad = int((got.view(np.uint32) != ref.view(np.uint32)).sum())
+        assert nbad == 0, f"{what}: within tolerance (max err {err:.3g}) but {nbad}/{ref.size} words not bit-identical"
+
+
+def make(pkg, orc, **kw):
+    return pkg.Modem(**kw), orc.OraclePath(**kw)
+
+
+def rand_bits(seed, F, nbits):
+    return np.random.default_rng(seed).integers(0, 2, (F, nbits), dtype=np.uint8)
+
+
+# ----------------------------------------------------------------------------- TX
+@pytest.mark.parametrize("scheme", MEMORYLESS)
+def test_tx_rect_all_schemes(pkg, orc, scheme):
+    """Rectangular-hold TX (exact reference semantics) for every memoryless -m scheme."""
+    kw = path_kwargs(scheme, sps=8)
+    m, o = make(pkg, orc, **kw)
+    bits = rand_bits(11, 3, 64 * o.bps + (o.bps - 1))  # ragged tail: the partial symbol is dropped
+    tx, iq = m.modulate(bits, want_iq=True)
+    tx_ref, iq_ref = o.modulate(bits, want_iq=True)
+    assert_buffers(iq, iq_ref, f"{scheme} baseband iq")
+    assert_buffers(tx, tx_ref, f"{scheme} tx")
+
+
+@pytest.mark.parametrize("sps,nsym", [(45, 101), (45, 100), (8, 513), (4, 77), (3, 333)])
+def test_tx_rect_shapes(pkg, orc, sps, nsym):
+    """Reference default rates (sps 45), odd frame lengths (scalar-store path), tile tails."""
+    kw = path_kwargs("qpsk", sps=sps)
+    m, o = make(pkg, orc, **kw)
+    bits = rand_bits(5, 4, nsym * 2)
+    assert_buffers(m.modulate(bits), o.modulate(bits), f"tx sps={sps} nsym={nsym}")
+
+
+def test_tx_sample0_and_many_frames(pkg, orc):
+    """Carrier counter carried over from a preamble (modulator.rs:9,66) and > frames_per_block frames."""
+    kw = path_kwargs("qpsk", sps=8, sample0=9 * 10 - 1)
+    m, o = make(pkg, orc, **kw)
+    bits = rand_bits(6, 70, 128)
+    assert_buffers(m.modulate(bits), o.modulate(bits), "tx sample0")
+
+
+def test_tx_large_sample_index(pkg, orc):
+    """n > 2^24: `s as f32` rounds (carrier.rs:18); the GPU must round the same way."""
+    kw = path_kwargs("qpsk", sps=8, sample0=(1 << 24) + 12345)
+    m, o = make(pkg, orc, **kw)
+    bits = rand_bits(8, 2, 256)
+    assert_buffers(m.modulate(bits), o.modulate(bits), "tx large n")
+
+
+@pytest.mark.parametrize("force_generic", [False, True])
+def test_tx_shaped_rrc(pkg, orc, force_generic, monkeypatch):
+    """129-tap RRC pulse shaping: fast (sps 8) and generic polyphase kernels."""
+    if force_generic:
+        monkeypatch.setenv("MODEM_GPU_FORCE_GENERIC", "1")
+    kw = path_kwargs("qpsk", sps=8, shaped=True)
+    m, o = make(pkg, orc, **kw)
+    bits = rand_bits(21, 5, 2 * 700)
+    if force_generic:
+        tx, iq = m.modulate(bits, want_iq=True)
+        tx_ref, iq_ref = o.modulate(bits, want_iq=True)
+        assert_buffers(iq, iq_ref, "rrc baseband")
+    else:
+        tx, tx_ref = m.modulate(bits), o.modulate(bits)
+    assert_buffers(tx, tx_ref, "rrc tx")
+
+
+@pytest.mark.parametrize("scheme,sps", [("qam16", 4), ("oqpsk", 10), ("dcqpsk", 5)])
+def test_tx_shaped_generic_schemes(pkg, orc, scheme, sps):
+    kw = path_kwargs(scheme, sps=sps, shaped=True)
+    m, o = make(pkg, orc, **kw)
+    bits = rand_bits(22, 3, o.bps * 150)
+    tx, iq = m.modulate(bits, want_iq=True)
+    tx_ref, iq_ref = o.modulate(bits, want_iq=True)
+    assert_buffers(iq, iq_ref, f"{scheme} shaped baseband")
+    assert_buffers(tx, tx_ref, f"{scheme} shaped tx")
+
+
+# ----------------------------------------------------------------------------- RX
+def _rx_check(m, o, rx, what, exact=True):
+    filt_ref, sym_ref, bits_ref = o.demodulate(rx)
+    out = m.demodulate(rx, want_filt=True, want_soft=True)
+    assert_buffers(out["filt"], filt_ref, what + " full-rate filtered (I,Q)", exact)
+    K = sym_ref.shape[1]
+    if K:
+        d, q = o.p.decision_delay, (o.sps // 2 if o.p.scheme == b"oqpsk" else 0)
+        soft_ref = np.stack([filt_ref[:, d::o.sps, 0][:, :K], filt_ref[:, d + q::o.sps, 1][:, :K]], axis=-1)
+        assert_buffers(out["soft"], soft_ref, what + " decision-instant (I,Q)", exact)
+    if exact:
+        assert np.array_equal(out["sym"], sym_ref), what + " symbol indices"
+        assert np.array_equal(out["bits"], bits_ref), what + " bits"
+    return out, sym_ref, bits_ref
+
+
+@pytest.mark.parametrize("scheme", MEMORYLESS)
+def test_loopback_all_schemes(pkg, orc, scheme):
+    """modulate -> demodulate for every memoryless scheme: buffers, symbols, bits."""
+    kw = path_kwargs(scheme, sps=8)
+    m, o = make(pkg, orc, **kw)
+    bits = rand_bits(31, 3, o.bps * 300)
+    tx = o.modulate(bits)
+    out, sym_ref, bits_ref = _rx_check(m, o, tx, scheme)
+    K = sym_ref.shape[1]
+    if scheme not in ("qam256",):  # 64-tap low-pass ISI closes the 256-QAM eye; parity still holds
+        assert np.array_equal(bits_ref, bits[:, : K * o.bps]), f"{scheme}: oracle round trip has bit errors"
+
+
+@pytest.mark.parametrize("force_generic", [False, True])
+@pytest.mark.parametrize("shaped", [False, True])
+def test_rx_fast_and_generic(pkg, orc, shaped, force_generic, monkeypatch):
+    """The fast sps-8 kernels (64-tap low-pass, 129-tap RRC) and the generic kernel agree with the oracle."""
+    if force_generic:
+        monkeypatch.setenv("MODEM_GPU_FORCE_GENERIC", "1")
+    kw = path_kwargs("qpsk", sps=8, shaped=shaped)
+    m, o = make(pkg, orc, **kw)
+    bits = rand_bits(41, 37, 2 * 1100)  # > frames_per_block frames, > 2 tiles of 512 symbols
+    tx = o.modulate(bits)
+    out, sym_ref, bits_ref = _rx_check(m, o, tx, f"shaped={shaped} generic={force_generic}")
+    K = sym_ref.shape[1]
+    assert np.array_equal(bits_ref, bits[:, : 2 * K])
+
+
+@pytest.mark.parametrize("sps,nsym", [(45, 120), (4, 301), (3, 100), (8, 9), (8, 4)])
+def test_rx_shapes(pkg, orc, sps, nsym):
+    """Reference default rates, odd lengths, frames shorter than the filter (K small or 0)."""
+    kw = path_kwargs("qpsk", sps=sps)
+    m, o = make(pkg, orc, **kw)
+    bits = rand_bits(43, 3, 2 * nsym)
+    _rx_check(m, o, o.modulate(bits), f"rx sps={sps} nsym={nsym}")
+
+
+def test_rx_phase_offset_and_sample0(pkg, orc):
+    """PLL::phase_offset != 0 (demodulator.rs:50) and a carried-over sample counter."""
+    kw = path_kwargs("qpsk", sps=8, phase_offset=0.3217, sample0=977)
+    m, o = make(pkg, orc, **kw)
+    bits = rand_bits(45, 4, 2 * 600)
+    _rx_check(m, o, o.modulate(bits), "phase_offset")
+
+
+def test_rx_arbitrary_input(pkg, orc):
+    """The demodulator on an arbitrary complex stream (not produced by our TX): only .re is read."""
+    kw = path_kwargs("qpsk", sps=8)
+    m, o = make(pkg, orc, **kw)
+    rng = np.random.default_rng(47)
+    rx = rng.standard_normal((3, 4096, 2)).astype(np.float32) * 3.0
+    _rx_check(m, o, rx, "arbitrary rx")
+    rx2 = rx.copy()
+    rx2[..., 1] = 0.0
+    a, b = m.demodulate(rx), m.demodulate(rx2)
+    assert np.array_equal(a["sym"], b["sym"])  # demodulator.rs:46 uses x.re only
+
+
+def test_fused_mac_flag_within_tolerance(pkg, orc):
+    """MODEM_FLAG_FUSED_MAC: FMA accumulation; not bit-identical, still inside the 1e-5 bar, same decisions."""
+    kw = path_kwargs("qpsk", sps=8, shaped=True)
+    o = orc.OraclePath(**kw)
+    m = pkg.Modem(flags=pkg.FLAG_FUSED_MAC, **kw)
+    bits = rand_bits(49, 6, 2 * 900)
+    tx_ref = o.modulate(bits)
+    assert_buffers(m.modulate(bits), tx_ref, "fma tx", exact=False)
+    out, sym_ref, bits_ref = _rx_check(m, o, tx_ref, "fma rx", exact=False)
+    assert np.array_equal(out["sym"], sym_ref) and np.array_equal(out["bits"], bits_ref)
+
+
+# ----------------------------------------------------------------------------- AWGN
+def test_awgn_matches_oracle(pkg, orc):
+    """Philox4x32-10 + Box-Muller stream: same counters, same noise (odd L, frame0 offset)."""
+    kw = path_kwargs("qpsk", sps=8)
+    m, o = make(pkg, orc, **kw)
+    buf = np.zeros((3, 1001, 2), np.float32)
+    got = m.awgn(buf, 0.75, seed=0xA5A5, frame0=(1 << 33) + 5)
+    ref = o.awgn(buf, 0.75, seed=0xA5A5, frame0=(1 << 33) + 5)
+    assert_buffers(got, ref, "awgn")
+    assert abs(float(got.std()) - 0.75) < 0.02
+
+
+@pytest.mark.parametrize("shaped", [False, True])
+def test_noisy_loopback_matches_oracle(pkg, orc, shaped):
+    """Loopback with the AWGN stage fused into the RX load: decisions and error counts equal the oracle's."""
+    kw = path_kwargs("qpsk", sps=8, shaped=shaped)
+    m, o = make(pkg, orc, **kw)
+    bits = rand_bits(51, 24, 2 * 1024)
+    sigma = o.sigma_for_ebn0(3.0)
+    assert m.sigma_for_ebn0(3.0) == sigma
+    sym_ref, bits_ref, cnt_ref = o.loopback(bits, sigma=sigma, seed=77, frame0=1000, threads=4)
+    out = m.loopback(bits, sigma=sigma, seed=77, frame0=1000, want_tx=True)
+    assert cnt_ref[0] > 0  # the test is only meaningful if noise flips some bits
+    assert np.array_equal(out["sym"], sym_ref)
+    assert np.array_equal(out["bits"], bits_ref)
+    assert (out["errors"], out["compared"]) == cnt_ref
+    # separate awgn + demodulate gives the same decisions as the fused load
+    noisy = m.awgn(out["tx"], sigma, seed=77, frame0=1000)
+    assert np.array_equal(m.demodulate(noisy)["sym"], sym_ref)
+
+
+# ----------------------------------------------------------------------------- banks, pointers, edges
+def test_multichannel_bank(pkg, orc):
+    """Independent carriers: frame f uses channel f // frames_per_channel (config 5 in miniature)."""
+    n_ch, fpc = 6, 3
+    hz = [500 + 4 * c * 37 for c in range(n_ch)]
+    kw = path_kwargs("qpsk", sps=8)
+    m = pkg.Modem(**kw)
+    m.set_channels([pkg.sample_freq(h, 10000) for h in hz], fpc)
+    bits = rand_bits(61, n_ch * fpc, 2 * 520)
+    tx = m.modulate(bits)
+    out = m.demodulate(tx, want_soft=True)
+    for c in range(n_ch):
+        kc = dict(kw, carrier_hz=hz[c])
+        o = orc.OraclePath(**kc)
+        sl = slice(c * fpc, (c + 1) * fpc)
+        tx_ref = o.modulate(bits[sl])
+        assert_buffers(tx[sl], tx_ref, f"channel {c} tx")
+        _, sym_ref, bits_ref = o.demodulate(tx_ref, want_filt=False)
+        assert np.array_equal(out["sym"][sl], sym_ref) and np.array_equal(out["bits"][sl], bits_ref)
+
+
+def test_device_pointers_torch(pkg, orc):
+    """Device-resident buffers (torch tensors) on torch's current stream."""
+    import torch
+
+    kw = path_kwargs("qpsk", sps=8)
+    m, o = make(pkg, orc, **kw)
+    m.set_stream(torch.cuda.current_stream().cuda_stream)
+    bits = rand_bits(71, 16, 2 * 2048)
+    F, nbits = bits.shape
+    L = m.frame_samples(nbits)
+    K = m.decided_symbols(L)
+    d_bits = torch.from_numpy(bits).cuda()
+    d_tx = torch.empty((F, L, 2), dtype=torch.float32, device="cuda")
+    d_sym = torch.empty((F, K), dtype=torch.uint8, device="cuda")
+    d_out = torch.empty((F, K * 2), dtype=torch.uint8, device="cuda")
+    err, cmp_ = m.loopback_into(d_bits, F, nbits, tx=d_tx, sym=d_sym, bits_out=d_out)
+    torch.cuda.synchronize()
+    tx_ref = o.modulate(bits)
+    _, sym_ref, bits_ref = o.demodulate(tx_ref, want_filt=False)
+    assert_buffers(d_tx.cpu().numpy(), tx_ref, "device tx")
+    assert np.array_equal(d_sym.cpu().numpy(), sym_ref)
+    assert np.array_equal(d_out.cpu().numpy(), bits_ref)
+    assert (err, cmp_) == (0, K * 2 * F)
+
+
+def test_empty_and_degenerate_inputs(pkg, orc):
+    kw = path_kwargs("qpsk", sps=8)
+    m, o = make(pkg, orc, **kw)
+    # no frames
+    assert m.modulate(np.zeros((0, 64), np.uint8)).shape == (0, 256, 2)
+    # fewer bits than one symbol: Bits yields Finished immediately (data.rs:58-62)
+    assert m.modulate(np.zeros((2, 1), np.uint8)).shape == (2, 0, 2)
+    # frame shorter than the decision delay: nothing decided
+    bits = rand_bits(81, 2, 2 * 4)
+    out = m.loopback(bits)
+    assert out["sym"].shape == (2, 0) and out["compared"] == 0
+    assert m.decided_symbols(35) == 0 and m.decided_symbols(36) == 1 == o.decided_symbols(36)
+
+
+# ----------------------------------------------------------------------------- full size
+def test_full_size_c2_properties(pkg, orc):
+    """BASELINE config 2 (4096 frames x 65536 samples, QPSK, sps 8, rect + 64-tap low-pass) at full
+    size: size-independent properties + sampled frames against the oracle."""
+    import torch
+
+    F, nsym = 4096, 8192
+    kw = path_kwargs("qpsk", sps=8)
+    m, o = make(pkg, orc, **kw)
+    m.set_stream(torch.cuda.current_stream().cuda_stream)
+    g = torch.Generator(device="cuda").manual_seed(1234)
+    d_bits = torch.randint(0, 2, (F, 2 * nsym), dtype=torch.uint8, device="cuda", generator=g)
+    L = m.frame_samples(2 * nsym)
+    K = m.decided_symbols(L)
+    assert (L, K) == (65536, 8188)
+    d_tx = torch.empty((F, L, 2), dtype=torch.float32, device="cuda")
+    d_sym = torch.empty((F, K), dtype=torch.uint8, device="cuda")
+    d_out = torch.empty((F, K * 2), dtype=torch.uint8, device="cuda")
+    err, cmp_ = m.loopback_into(d_bits, F, 2 * nsym, tx=d_tx, sym=d_sym, bits_out=d_out)
+    torch.cuda.synchronize()
+    # round trip: every decided bit equals the transmitted bit, and the counters say so
+    assert (err, cmp_) == (0, F * K * 2)
+    assert torch.equal(d_out, d_bits[:, : 2 * K])
+    # symbol indices are the MSB-first packing of the bits
+    assert torch.equal(d_sym, d_out[:, 0::2] * 2 + d_out[:, 1::2])
+    # constant envelope: |tx| == amplitude for QPSK
+    mag = torch.linalg.vector_norm(d_tx[::257], dim=-1)
+    assert float((mag - 1.0).abs().max()) < 1e-6
+    # sampled frames against the oracle (first, last, a few in between)
+    idx = [0, 1, 31, 32, 2047, 4095]
+    bits_s = d_bits[idx].cpu().numpy()
+    tx_ref = o.modulate(bits_s)
+    assert_buffers(d_tx[idx].cpu().numpy(), tx_ref, "C2 sampled tx")
+    _, sym_ref, _ = o.demodulate(tx_ref, want_filt=False)
+    assert np.array_equal(d_sym[idx].cpu().numpy(), sym_ref)
