@@ -1,0 +1,31 @@
+/*
+ * launch.h -- host-side launchers of the compile-time specialised kernels (each lives in
+ * its own translation unit so the build parallelises).  Every launcher returns false when
+ * it has no instantiation for the requested shape; the caller then uses the generic kernel.
+ */
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include "common.cuh"
+
+namespace mg {
+
+struct LaunchGeom {
+    uint64_t tiles_x;   /* filled by *_tiles(): CTAs along the sample axis */
+};
+
+/* rx_fast_<NT>.cu: sps 8, NT taps.  `variant` picks a tuning variant (0 = default). */
+bool rx_fast_supported(uint32_t n_taps);
+uint64_t rx_fast_tiles(uint32_t n_taps, uint64_t K, int variant);
+cudaError_t rx_fast_launch(const RxArgs& a, const float* h_taps, bool fma, int variant, cudaStream_t stream);
+
+/* tx_fast.cu */
+bool tx_rect_fast_supported(uint32_t bps);
+uint64_t tx_rect_fast_tiles(uint64_t L);
+cudaError_t tx_rect_fast_launch(const TxArgs& a, cudaStream_t stream);
+bool tx_shaped_fast_supported(uint32_t sps, uint32_t n_taps);
+uint64_t tx_shaped_fast_tiles(uint64_t nsym);
+cudaError_t tx_shaped_fast_launch(const TxArgs& a, const float* h_taps, bool fma, cudaStream_t stream);
+
+} /* namespace mg */

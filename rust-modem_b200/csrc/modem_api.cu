@@ -15,6 +15,7 @@
 
 #include "../../include/modem_gpu.h"
 #include "kernels.cuh"
+#include "launch.h"
 
 using mg::u64;
 
@@ -45,6 +46,7 @@ struct modem_ctx {
     Scratch s_bits, s_tx, s_iq, s_rx, s_sym, s_bits_out, s_soft, s_filt;
     uint64_t launches = 0;
     bool force_generic = false;
+    int rx_variant = 0; /* MODEM_GPU_RX_VARIANT: tuning knob, 0 = default */
     std::string last_error;
 };
 
@@ -170,14 +172,6 @@ uint32_t frames_per_block(const modem_ctx* ctx, u64 F, u64 tiles_x)
     return (uint32_t)fpb;
 }
 
-template <int NT>
-mg::TapsParam<NT> taps_param(const std::vector<float>& h)
-{
-    mg::TapsParam<NT> t;
-    for (int i = 0; i < NT; ++i) t.h[i] = h[i];
-    return t;
-}
-
 bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 /* ------------------------------------------------------------------ TX launch */
@@ -208,21 +202,27 @@ int launch_tx(modem_ctx* ctx, const uint8_t* d_bits, u64 F, u64 nbits, float2* d
     const bool vec_ok = (a.L % 2 == 0) && aligned16(d_tx) && aligned16(d_iq);
 
     if (c.n_tx_taps == 0) {
-        const int vec = vec_ok ? 2 : 1;
-        const u64 tile = (u64)mg::kThreads * 2 * vec;
-        const u64 tiles = (a.L + tile - 1) / tile;
-        a.frames_per_block = frames_per_block(ctx, F, tiles);
-        dim3 grid((unsigned)tiles, (unsigned)((F + a.frames_per_block - 1) / a.frames_per_block));
-        if (vec == 2) mg::tx_rect_kernel<2><<<grid, mg::kThreads, 0, ctx->stream>>>(a);
-        else mg::tx_rect_kernel<1><<<grid, mg::kThreads, 0, ctx->stream>>>(a);
-    } else if (!ctx->force_generic && c.samples_per_symbol == 8 && c.n_tx_taps == 129 && c.q_offset == 0 && d_tx &&
-               !d_iq && vec_ok) {
-        const u64 tiles = (a.nsym + mg::kThreads - 1) / mg::kThreads;
-        a.frames_per_block = frames_per_block(ctx, F, tiles);
-        dim3 grid((unsigned)tiles, (unsigned)((F + a.frames_per_block - 1) / a.frames_per_block));
-        auto tp = taps_param<129>(ctx->h_tx_taps);
-        if (fma) mg::tx_shaped_fast_kernel<8, 129, true><<<grid, mg::kThreads, 0, ctx->stream>>>(a, tp);
-        else mg::tx_shaped_fast_kernel<8, 129, false><<<grid, mg::kThreads, 0, ctx->stream>>>(a, tp);
+        const uint32_t bps = c.bits_per_symbol;
+        const bool word_ok = mg::tx_rect_fast_supported(bps) && (nbits % bps == 0) &&
+                             ((reinterpret_cast<uintptr_t>(d_bits) % bps) == 0);
+        const bool fast = !ctx->force_generic && vec_ok && d_tx && !d_iq && c.q_offset == 0 && c.n_tables == 1 &&
+                          (c.samples_per_symbol % 2 == 0) && word_ok && a.L < (1ull << 32);
+        if (fast) {
+            a.frames_per_block = frames_per_block(ctx, F, mg::tx_rect_fast_tiles(a.L));
+            CK(ctx, mg::tx_rect_fast_launch(a, ctx->stream));
+        } else {
+            const int vec = vec_ok ? 2 : 1;
+            const u64 tile = (u64)mg::kThreads * 2 * vec;
+            const u64 tiles = (a.L + tile - 1) / tile;
+            a.frames_per_block = frames_per_block(ctx, F, tiles);
+            dim3 grid((unsigned)tiles, (unsigned)((F + a.frames_per_block - 1) / a.frames_per_block));
+            if (vec == 2) mg::tx_rect_kernel<2><<<grid, mg::kThreads, 0, ctx->stream>>>(a);
+            else mg::tx_rect_kernel<1><<<grid, mg::kThreads, 0, ctx->stream>>>(a);
+        }
+    } else if (!ctx->force_generic && mg::tx_shaped_fast_supported(c.samples_per_symbol, c.n_tx_taps) && c.q_offset == 0 &&
+               d_tx && !d_iq && vec_ok) {
+        a.frames_per_block = frames_per_block(ctx, F, mg::tx_shaped_fast_tiles(a.nsym));
+        CK(ctx, mg::tx_shaped_fast_launch(a, ctx->h_tx_taps.data(), fma, ctx->stream));
     } else {
         const uint32_t sps = c.samples_per_symbol, N = c.n_tx_taps;
         uint32_t TS = std::max<uint32_t>(1, std::min<uint32_t>(256, 2048 / sps));
@@ -247,24 +247,6 @@ int launch_tx(modem_ctx* ctx, const uint8_t* d_bits, u64 F, u64 nbits, float2* d
 }
 
 /* ------------------------------------------------------------------ RX launch */
-template <int NT>
-int launch_rx_fast(modem_ctx* ctx, mg::RxArgs& a, bool fma)
-{
-    using C = mg::RxFastCfg<8, NT>;
-    const u64 tiles = (a.K + C::TS - 1) / C::TS;
-    a.frames_per_block = frames_per_block(ctx, a.F, tiles);
-    dim3 grid((unsigned)tiles, (unsigned)((a.F + a.frames_per_block - 1) / a.frames_per_block));
-    auto tp = taps_param<NT>(ctx->h_rx_taps);
-    if (fma) {
-        CK(ctx, cudaFuncSetAttribute(mg::rx_fast_kernel<8, NT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
-        mg::rx_fast_kernel<8, NT, true><<<grid, mg::kThreads, C::SMEM, ctx->stream>>>(a, tp);
-    } else {
-        CK(ctx, cudaFuncSetAttribute(mg::rx_fast_kernel<8, NT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
-        mg::rx_fast_kernel<8, NT, false><<<grid, mg::kThreads, C::SMEM, ctx->stream>>>(a, tp);
-    }
-    return MODEM_OK;
-}
-
 int launch_rx(modem_ctx* ctx, const float2* d_rx, u64 F, u64 L, uint8_t* d_sym, uint8_t* d_bits, float2* d_soft,
               float2* d_filt, const uint8_t* d_ref, u64 ref_stride, u64* d_counters, float sigma, uint64_t seed,
               uint64_t frame0)
@@ -319,13 +301,11 @@ int launch_rx(modem_ctx* ctx, const float2* d_rx, u64 F, u64 L, uint8_t* d_sym, 
     }
     if (a.K == 0 || !(d_sym || d_bits || d_soft || d_ref)) return MODEM_OK;
 
-    const bool fast_ok = !ctx->force_generic && sps == 8 && c.q_offset == 0 && (L % 2 == 0) && aligned16(d_rx);
-    if (fast_ok && N == 64) {
-        int rc = launch_rx_fast<64>(ctx, a, fma);
-        if (rc) return rc;
-    } else if (fast_ok && N == 129) {
-        int rc = launch_rx_fast<129>(ctx, a, fma);
-        if (rc) return rc;
+    const bool fast_ok = !ctx->force_generic && sps == 8 && c.q_offset == 0 && (L % 2 == 0) && aligned16(d_rx) &&
+                         mg::rx_fast_supported(N);
+    if (fast_ok) {
+        a.frames_per_block = frames_per_block(ctx, F, mg::rx_fast_tiles(N, a.K, ctx->rx_variant));
+        CK(ctx, mg::rx_fast_launch(a, ctx->h_rx_taps.data(), fma, ctx->rx_variant, ctx->stream));
     } else {
         const size_t budget = 96 * 1024;
         if ((size_t)N * 4 + (size_t)(N + c.q_offset) * 16 > budget)
@@ -449,6 +429,8 @@ int modem_gpu_create(modem_ctx_t** out, int device, const modem_cfg_t* cfg)
     ctx->cfg.tx_taps = cfg->n_tx_taps ? ctx->h_tx_taps.data() : nullptr;
     const char* fg = getenv("MODEM_GPU_FORCE_GENERIC");
     ctx->force_generic = fg && fg[0] == '1';
+    const char* rv = getenv("MODEM_GPU_RX_VARIANT");
+    ctx->rx_variant = rv ? atoi(rv) : 0;
 
     rc = MODEM_OK;
     cudaError_t e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);

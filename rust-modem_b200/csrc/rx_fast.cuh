@@ -1,0 +1,335 @@
+/*
+ * rx_fast.cuh -- fast decimating RX for 8 samples per symbol and a compile-time tap count NT:
+ * the hot kernel of the loopback (replaces demodulator.rs:44-55 + two fir.rs:18-34 filters
+ * of the reference, plus the decimator / slicer / error-count extension).
+ *
+ * The tile is a run of 8-sample BLOCKS; block B holds tile-local samples [8B, 8B+7].  The
+ * decision instant of tile symbol r sits at position 7-OFF of block r+NB-1 (OFF = 0 for an
+ * odd decision delay, 1 for an even one, so that blocks coincide with the 16-byte aligned
+ * sample pairs global memory is read in), and tap i of symbol r reads element e of block
+ * r+NB-1-b with i = 8b + 7 - OFF - e.
+ *
+ *  phase A  the tile's global loads (128-bit, two complex samples; the next frame's tile was
+ *           prefetched towards L2 during the previous FIR) are all issued before the first
+ *           use; the real parts are multiplied by the CTA-resident (cos, -sin) table and
+ *           stored as interleaved (vi, vq) pairs: one 128-bit shared store per pair;
+ *  phase B  every thread owns R consecutive symbols and walks its NB+R-1 blocks ONCE, newest
+ *           first: a block is loaded into registers one step ahead (conflict-free 128-bit
+ *           shared loads at thread_base + compile-time offset) and feeds all R symbols, each
+ *           with its own compile-time tap group, so every accumulator still sees taps
+ *           0..NT-1 in order; taps are constant-bank operands.  Shared traffic of the FIR is
+ *           (NB+R-1)*64 B per R symbols: 22 B/sample at R = 4, NT = 64;
+ *  phase C  slice, pack, count errors; one 32-bit symbol store and one 64-bit bit store.
+ *
+ * Shared layout: 16-byte chunk c (samples 2c, 2c+1) lives at chunk position c + c/(4R): one
+ * chunk of padding per thread stride, so the 8 lanes of a quarter warp (stride 4R chunks in
+ * phase B, stride 1 in phase A) always hit 8 distinct bank groups.
+ */
+#pragma once
+
+#include "common.cuh"
+
+namespace mg {
+
+template <int NT, int OFF, int THREADS, int R>
+struct RxFastCfg {
+    static constexpr int NB = (NT + OFF + 7) / 8; /* blocks that reach one symbol */
+    static constexpr int TS = R * THREADS;        /* symbols per tile */
+    static constexpr int NBLK = TS + NB - 1;      /* blocks staged per tile */
+    static constexpr int NSAMP = NBLK * 8;
+    static constexpr int NCHUNK = NSAMP / 2;      /* 16-byte chunks */
+    static constexpr int PADW = 4 * R;            /* one padding chunk per PADW chunks */
+    static constexpr int PCHUNK = NCHUNK + NCHUNK / PADW + 1;
+    static constexpr int ITER = (NCHUNK + THREADS - 1) / THREADS;
+    static constexpr int NSTEP = NB + R - 1;      /* blocks one thread walks */
+    static constexpr size_t SMEM_V = sizeof(float4) * PCHUNK;
+    static constexpr size_t SMEM_CS = sizeof(float4) * NCHUNK;
+    static size_t smem(uint32_t lut_entries) { return SMEM_V + SMEM_CS + sizeof(float2) * lut_entries; }
+    static_assert(THREADS % PADW == 0, "phase A position arithmetic needs THREADS % (4R) == 0");
+};
+
+/* nearest point over a table in shared memory, four candidates per trip */
+__device__ __forceinline__ uint32_t slice_point4(const float2* t, uint32_t n, float I, float Q)
+{
+    if (n < 4) return slice_point(t, n, I, Q);
+    uint32_t best = 0;
+    float bd = 0.0f;
+    for (uint32_t s = 0; s < n; s += 4) {
+        float d[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float2 c = t[s + j];
+            const float di = __fsub_rn(I, c.x), dq = __fsub_rn(Q, c.y);
+            d[j] = __fadd_rn(__fmul_rn(di, di), __fmul_rn(dq, dq));
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            if ((s + j == 0) || d[j] < bd) {
+                bd = d[j];
+                best = s + j;
+            }
+    }
+    return best;
+}
+
+template <int NT, int OFF, bool FMA, bool NOISE, int THREADS, int MINB, int R, int PF>
+__global__ void __launch_bounds__(THREADS, MINB)
+    rx_fast_kernel(const __grid_constant__ RxArgs a, const __grid_constant__ TapsParam<NT> taps)
+{
+    using C = RxFastCfg<NT, OFF, THREADS, R>;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float4* s_v = reinterpret_cast<float4*>(smem_raw); /* padded chunks of (vi0,vq0,vi1,vq1) */
+    float4* s_cs = s_v + C::PCHUNK;                     /* per chunk: (c0,-s0,c1,-s1) */
+    float2* s_slut = reinterpret_cast<float2*>(s_cs + C::NCHUNK);
+
+    const int tid = threadIdx.x;
+    for (uint32_t i = tid; i < a.n_tables * a.n_const; i += THREADS) s_slut[i] = a.slut[i];
+
+    const u64 f0 = (u64)blockIdx.y * a.frames_per_block;
+    const u64 f1 = min(a.F, f0 + a.frames_per_block);
+    const float w = chan_w(a.ch, f0), po = chan_po(a.ch, f0);
+    const u64 k0 = (u64)blockIdx.x * C::TS;
+    /* sample index of tile-local j = 0; even by the choice of OFF */
+    const long long nbase = (long long)(k0 * 8 + a.delay) + OFF - 8 * C::NB + 1;
+    const bool interior = nbase >= 0 && (u64)(nbase + C::NSAMP) <= a.L;
+
+    for (int q = tid; q < C::NCHUNK; q += THREADS) {
+        float v[4];
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            long long n = nbase + 2 * q + e;
+            float s = 0.0f, c = 0.0f;
+            if (n >= 0 && (u64)n < a.L) mg_sincosf(__fadd_rn(nco_phase(w, a.sample0 + (u64)n), po), &s, &c);
+            v[2 * e] = c;
+            v[2 * e + 1] = -s;
+        }
+        s_cs[q] = make_float4(v[0], v[1], v[2], v[3]);
+    }
+
+    const u64 ka = k0 + (u64)R * tid; /* this thread's symbols: ka .. ka+R-1 */
+    uint32_t toff[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) toff[r] = (uint32_t)((ka + r) % a.n_tables) * a.n_const;
+    const bool have_any = ka < a.K, have_all = ka + R <= a.K;
+    /* vector emit: every frame's symbol row must start on a multiple of R symbols */
+    const bool vec_out = a.bps == 2 && have_all && (a.K % R == 0) &&
+                         ((reinterpret_cast<uintptr_t>(a.sym) % R) == 0) &&
+                         ((reinterpret_cast<uintptr_t>(a.bits) % (2 * R)) == 0);
+    const bool ref_vec = a.ref_bits && vec_out && (a.ref_stride % (2 * R) == 0) &&
+                         ((reinterpret_cast<uintptr_t>(a.ref_bits) % (2 * R)) == 0);
+
+    uint32_t err = 0, cmp = 0;
+    const int wbase = tid + tid / C::PADW;              /* phase A: chunk position of chunk `tid` */
+    const ulonglong2* rbase = reinterpret_cast<const ulonglong2*>(s_v) + (C::PADW + 1) * tid; /* phase B: chunk position of chunk 4R*tid */
+    const f32x2 one = pk2(taps.one.x, taps.one.y);
+    const float2* frame = a.rx + f0 * a.L;
+    u64 orow = f0 * a.K + ka; /* output index of symbol ka in the current frame */
+    const uint8_t* refp = a.ref_bits ? a.ref_bits + f0 * a.ref_stride + ka * 2 : nullptr;
+    float xr[C::ITER][2]; /* real parts of the tile being staged (PF == 2: of the NEXT frame, in flight during the FIR) */
+    auto load_tile = [&](const float2* fr) {
+        if (interior) {
+            const float4* src = reinterpret_cast<const float4*>(fr + nbase) + tid;
+#pragma unroll
+            for (int it = 0; it < C::ITER; ++it) {
+                if (it * THREADS + tid < C::NCHUNK) {
+                    const float4 t = __ldcs(src + it * THREADS);
+                    xr[it][0] = t.x;
+                    xr[it][1] = t.z;
+                }
+            }
+        } else {
+#pragma unroll
+            for (int it = 0; it < C::ITER; ++it) {
+                const long long n = nbase + 2 * (it * THREADS + tid);
+                xr[it][0] = 0.0f;
+                xr[it][1] = 0.0f;
+                if (it * THREADS + tid < C::NCHUNK) {
+                    if (n >= 0 && (u64)n < a.L) xr[it][0] = __ldcs(&fr[n].x);
+                    if (n + 1 >= 0 && (u64)(n + 1) < a.L) xr[it][1] = __ldcs(&fr[n + 1].x);
+                }
+            }
+        }
+    };
+    if (PF == 2 && f0 < f1) load_tile(frame);
+    for (u64 f = f0; f < f1; ++f, orow += a.K, frame += a.L) {
+        __syncthreads(); /* previous frame's phase B finished; s_cs / s_slut visible */
+        /* ---- phase A: load the tile (all loads issued before the first use), mix, stage */
+        if (PF != 2) load_tile(frame);
+        if (NOISE) {
+            const u64 gf = a.nz.frame0 + f;
+#pragma unroll 1
+            for (int it = 0; it < C::ITER; ++it) {
+                const long long n = nbase + 2 * (it * THREADS + tid);
+                if (it * THREADS + tid < C::NCHUNK) {
+                    float n0 = 0.0f, n1 = 0.0f;
+                    const bool v0 = n >= 0 && (u64)n < a.L, v1 = n + 1 >= 0 && (u64)(n + 1) < a.L;
+                    if (v0) n0 = noise_re(a.nz, gf, (u64)n);
+                    if (v1) n1 = noise_re(a.nz, gf, (u64)(n + 1));
+                    /* xr[] must be indexed statically to stay in registers */
+#pragma unroll
+                    for (int j = 0; j < C::ITER; ++j)
+                        if (j == it) {
+                            if (v0) xr[j][0] = __fadd_rn(xr[j][0], __fmul_rn(a.nz.sigma, n0));
+                            if (v1) xr[j][1] = __fadd_rn(xr[j][1], __fmul_rn(a.nz.sigma, n1));
+                        }
+                }
+            }
+        }
+#pragma unroll
+        for (int it = 0; it < C::ITER; ++it) {
+            if (it * THREADS + tid < C::NCHUNK) {
+                const float4 cs = s_cs[it * THREADS + tid];
+                /* chunk q = it*THREADS + tid  ->  position q + q/PADW = wbase + it*(THREADS + THREADS/PADW) */
+                s_v[wbase + it * (THREADS + THREADS / C::PADW)] =
+                    make_float4(__fmul_rn(xr[it][0], cs.x), __fmul_rn(xr[it][0], cs.y), __fmul_rn(xr[it][1], cs.z),
+                                __fmul_rn(xr[it][1], cs.w));
+            }
+        }
+        __syncthreads();
+        if (PF == 2 && f + 1 < f1) load_tile(frame + a.L); /* next frame's loads fly during the FIR */
+        /* pull the next frame's tile towards L2 while the FIR runs: PF 1 = one prefetch per 128-byte
+         * line through the LSU, PF 3 = one bulk (TMA) L2 prefetch of the whole tile by one thread */
+        if (PF == 1 && f + 1 < f1 && interior) {
+            const char* nxt = reinterpret_cast<const char*>(frame + a.L + nbase);
+            for (int o = tid * 128; o < C::NSAMP * 8; o += THREADS * 128)
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(nxt + o));
+        }
+        if (PF == 3 && f + 1 < f1 && interior && tid == 0) {
+            const char* nxt = reinterpret_cast<const char*>(frame + a.L + nbase);
+            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(nxt), "r"(C::NSAMP * 8) : "memory");
+        }
+        uint2 refw = make_uint2(0u, 0u);
+        if (ref_vec) {
+            if (R == 4) refw = __ldg(reinterpret_cast<const uint2*>(refp));
+            else refw.x = __ldg(reinterpret_cast<const uint32_t*>(refp));
+        }
+
+        /* ---- phase B: one pass over the thread's NB+R-1 blocks, newest first; block m (relative to
+         * block R*tid) feeds symbol ka+r with tap group b = r - m + NB - 1.  (vi, vq) of a sample
+         * is one packed pair; a MAC on both rails is FMUL2 + FFMA2 (common.cuh, f32x2). */
+        f32x2 acc[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) acc[r] = 0ull; /* (+0.0f, +0.0f) */
+        if (have_any) {
+            f32x2 cv[8], nv[8];
+            auto load_block = [&](f32x2* dst, int m) {
+                /* chunks 4R*tid + 4m + i  ->  position (4R+1)*tid + x + x/PADW, x = 4m + i */
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int x = 4 * m + i;
+                    const ulonglong2 t = rbase[x + x / C::PADW];
+                    dst[2 * i + 0] = t.x;
+                    dst[2 * i + 1] = t.y;
+                }
+            };
+            load_block(cv, C::NSTEP - 1);
+#pragma unroll
+            for (int s = 0; s < C::NSTEP; ++s) {
+                const int m = C::NSTEP - 1 - s;
+                if (s + 1 < C::NSTEP) load_block(nv, m - 1); /* one block ahead of its use */
+#pragma unroll
+                for (int e = 7; e >= 0; --e) {
+#pragma unroll
+                    for (int r = 0; r < R; ++r) {
+                        const int b = r - m + C::NB - 1;
+                        const int i = 8 * b + 7 - OFF - e; /* tap index, ascending as e descends */
+                        if (b >= 0 && b < C::NB && i >= 0 && i < NT)
+                            acc[r] = mac2<FMA>(acc[r], cv[e], pk2(taps.hh[i].x, taps.hh[i].y), one);
+                    }
+                }
+#pragma unroll
+                for (int e = 0; e < 8; ++e) cv[e] = nv[e];
+            }
+        }
+        float ai[R], aq[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const float2 t = unpk2(acc[r]);
+            ai[r] = t.x;
+            aq[r] = t.y;
+        }
+        /* ---- phase C */
+        if (vec_out) {
+            uint32_t symw = 0, bitw[2] = {0u, 0u}, nerr = 0;
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                const float I = __fmul_rn(a.rx_gain, ai[r]), Q = __fmul_rn(a.rx_gain, aq[r]);
+                const uint32_t s = slice_point4(s_slut + toff[r], a.n_const, I, Q);
+                symw |= s << (8 * r);
+                bitw[r / 2] |= ((s >> 1) | ((s & 1u) << 8)) << (16 * (r % 2));
+                if (a.soft) a.soft[orow + r] = make_float2(I, Q);
+                if (a.ref_bits) {
+                    uint32_t ref;
+                    if (ref_vec) {
+                        const uint32_t wd = (r / 2) ? refw.y : refw.x;
+                        const uint32_t h = wd >> (16 * (r % 2));
+                        ref = ((h & 1u) << 1) | ((h >> 8) & 1u);
+                    } else {
+                        ref = pack_symbol(refp + 2 * r, 2);
+                    }
+                    nerr += __popc(ref ^ s);
+                }
+            }
+            if (a.sym) {
+                if (R == 4) *reinterpret_cast<uint32_t*>(a.sym + orow) = symw;
+                else *reinterpret_cast<uint16_t*>(a.sym + orow) = (uint16_t)symw;
+            }
+            if (a.bits) {
+                if (R == 4) *reinterpret_cast<uint2*>(a.bits + 2 * orow) = make_uint2(bitw[0], bitw[1]);
+                else *reinterpret_cast<uint32_t*>(a.bits + 2 * orow) = bitw[0];
+            }
+            if (a.ref_bits) {
+                err += nerr;
+                cmp += 2 * R;
+            }
+        } else if (have_any) {
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                if (ka + r < a.K) {
+                    const float I = __fmul_rn(a.rx_gain, ai[r]), Q = __fmul_rn(a.rx_gain, aq[r]);
+                    const uint32_t s = slice_point4(s_slut + toff[r], a.n_const, I, Q);
+                    err += emit_symbol(a, f, ka + r, s, I, Q);
+                    cmp += a.ref_bits ? a.bps : 0u;
+                }
+            }
+        }
+        if (refp) refp += a.ref_stride;
+    }
+    block_count(a, err, cmp);
+}
+
+/* ------------------------------------------------------------------ host side */
+template <int NT, int OFF, bool FMA, bool NOISE, int THREADS, int MINB, int R, int PF = RX_DEFAULT_PF>
+cudaError_t rx_fast_launch_t(const RxArgs& a, const float* h_taps, cudaStream_t stream)
+{
+    using C = RxFastCfg<NT, OFF, THREADS, R>;
+    dim3 grid((unsigned)((a.K + C::TS - 1) / C::TS), (unsigned)((a.F + a.frames_per_block - 1) / a.frames_per_block));
+    const TapsParam<NT> tp = make_taps_param<NT>(h_taps);
+    const size_t smem = C::smem(a.n_tables * a.n_const);
+    auto kern = rx_fast_kernel<NT, OFF, FMA, NOISE, THREADS, MINB, R, PF>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    if (e != cudaSuccess) return e;
+    kern<<<grid, THREADS, smem, stream>>>(a, tp);
+    return cudaGetLastError();
+}
+
+/* all (OFF, FMA, NOISE) combinations of one (NT, THREADS, MINB) */
+template <int NT, int THREADS, int MINB, int R>
+cudaError_t rx_fast_dispatch(const RxArgs& a, const float* h_taps, bool fma, cudaStream_t stream)
+{
+    const bool odd = (a.delay & 1u) != 0; /* OFF = 0 for odd delay, 1 for even */
+    const bool noise = a.nz.sigma != 0.0f;
+#define MG_RX_CASE(O, F, N) return rx_fast_launch_t<NT, O, F, N, THREADS, MINB, R>(a, h_taps, stream)
+    if (odd) {
+        if (fma) { if (noise) MG_RX_CASE(0, true, true); else MG_RX_CASE(0, true, false); }
+        else     { if (noise) MG_RX_CASE(0, false, true); else MG_RX_CASE(0, false, false); }
+    } else {
+        if (fma) { if (noise) MG_RX_CASE(1, true, true); else MG_RX_CASE(1, true, false); }
+        else     { if (noise) MG_RX_CASE(1, false, true); else MG_RX_CASE(1, false, false); }
+    }
+#undef MG_RX_CASE
+}
+
+} /* namespace mg */

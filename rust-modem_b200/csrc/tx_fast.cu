@@ -1,0 +1,192 @@
+/*
+ * tx_fast.cu -- compile-time specialised TX kernels (rectangular hold with word-wise bit
+ * loads; 129-tap pulse shaping at 8 samples per symbol) and their launchers.
+ */
+#include "launch.h"
+
+namespace mg {
+
+/*
+ * Fast rectangular-hold TX: one table, no Q offset, even sps (both samples of a 128-bit
+ * store share a symbol), bits rows aligned to BPS bytes.  The frame loop is unrolled by FU
+ * with all bit loads of the batch issued first, so FU*U independent loads are in flight
+ * per thread instead of one dependent chain per frame.
+ */
+template <int BPS>
+__global__ void __launch_bounds__(kThreads, 4) tx_rect_fast_kernel(const __grid_constant__ TxArgs a)
+{
+    constexpr int U = 2, FU = 4;
+    __shared__ float2 s_lut[1 << BPS];
+    for (uint32_t i = threadIdx.x; i < (1u << BPS); i += kThreads) s_lut[i] = a.lut[i];
+    __syncthreads();
+
+    const u64 f0 = (u64)blockIdx.y * a.frames_per_block;
+    const u64 f1 = min(a.F, f0 + a.frames_per_block);
+    const float w = chan_w(a.ch, f0);
+
+    uint32_t koff[U]; /* byte offset of the symbol's bits inside a frame row */
+    uint32_t noff[U]; /* float4 offset of the sample pair inside a frame row */
+    bool valid[U];
+    float c0[U], s0[U], c1[U], s1[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        const uint32_t pair = ((uint32_t)blockIdx.x * U + u) * kThreads + threadIdx.x;
+        const u64 n = 2 * (u64)pair;
+        valid[u] = n < a.L;
+        noff[u] = pair;
+        koff[u] = (uint32_t)(n / a.sps) * BPS;
+        mg_sincosf(nco_phase(w, a.sample0 + n), &s0[u], &c0[u]);
+        mg_sincosf(nco_phase(w, a.sample0 + n + 1), &s1[u], &c1[u]);
+    }
+
+    const uint8_t* pb = a.bits + f0 * a.nbits;
+    float4* po = reinterpret_cast<float4*>(a.tx + f0 * a.L);
+    const u64 Lq = a.L / 2; /* float4 per frame row */
+    u64 f = f0;
+    for (; f + FU <= f1; f += FU) {
+        uint32_t idx[FU][U];
+#pragma unroll
+        for (int j = 0; j < FU; ++j)
+#pragma unroll
+            for (int u = 0; u < U; ++u) idx[j][u] = valid[u] ? load_symbol_word<BPS>(pb + j * a.nbits + koff[u]) : 0u;
+#pragma unroll
+        for (int j = 0; j < FU; ++j)
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const float2 bb = s_lut[idx[j][u]];
+                const float2 o0 = mix_iq(bb.x, bb.y, c0[u], s0[u]);
+                const float2 o1 = mix_iq(bb.x, bb.y, c1[u], s1[u]);
+                if (valid[u]) __stcs(po + j * Lq + noff[u], make_float4(o0.x, o0.y, o1.x, o1.y));
+            }
+        pb += FU * a.nbits;
+        po += FU * Lq;
+    }
+    for (; f < f1; ++f) {
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            if (!valid[u]) continue;
+            const float2 bb = s_lut[load_symbol_word<BPS>(pb + koff[u])];
+            const float2 o0 = mix_iq(bb.x, bb.y, c0[u], s0[u]);
+            const float2 o1 = mix_iq(bb.x, bb.y, c1[u], s1[u]);
+            __stcs(po + noff[u], make_float4(o0.x, o0.y, o1.x, o1.y));
+        }
+        pb += a.nbits;
+        po += Lq;
+    }
+}
+
+/*
+ * Fast pulse-shaped TX for compile-time (SPS, NT): one thread owns one symbol period
+ * (SPS consecutive samples).  The J = ceil(NT/SPS) symbols that reach it sit in registers,
+ * the taps are kernel-parameter constants (constant-bank operands, no load instructions),
+ * and the CTA's 2 KB-per-warp output is transposed through shared memory so that global
+ * stores are full 128-bit coalesced.
+ */
+template <int SPS, int NT, bool FMA>
+__global__ void __launch_bounds__(kThreads)
+    tx_shaped_fast_kernel(const __grid_constant__ TxArgs a, const __grid_constant__ TapsParam<NT> taps)
+{
+    static_assert(SPS == 8, "output transpose below is written for 8 samples per symbol");
+    constexpr int J = (NT + SPS - 1) / SPS; /* symbols reaching one output */
+    constexpr int HALO = J - 1;
+    __shared__ float2 s_lut[kMaxLut];
+    __shared__ __align__(8) float2 s_sym[2][kThreads + HALO];
+    __shared__ __align__(16) float4 s_out[kThreads / 32][32 * SPS / 2]; /* per warp: 32 symbols x 8 samples x 8 B */
+
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    for (uint32_t i = tid; i < a.n_tables * a.n_const; i += kThreads) s_lut[i] = a.lut[i];
+    const f32x2 one = pk2(taps.one.x, taps.one.y);
+
+    const u64 f0 = (u64)blockIdx.y * a.frames_per_block;
+    const u64 f1 = min(a.F, f0 + a.frames_per_block);
+    const float w = chan_w(a.ch, f0);
+    const u64 k0 = (u64)blockIdx.x * kThreads; /* first symbol of the tile */
+    const u64 m = k0 + tid;                    /* this thread's symbol */
+
+    float cs[SPS], sn[SPS];
+#pragma unroll
+    for (int p = 0; p < SPS; ++p) mg_sincosf(nco_phase(w, a.sample0 + m * SPS + p), &sn[p], &cs[p]);
+
+    auto stage = [&](int buf, u64 f) {
+        const uint8_t* fb = a.bits + f * a.nbits;
+        for (int i = tid; i < kThreads + HALO; i += kThreads) {
+            long long mm = (long long)k0 - HALO + i;
+            float2 v = make_float2(0.0f, 0.0f);
+            if (mm >= 0 && (u64)mm < a.nsym)
+                v = s_lut[((u64)mm % a.n_tables) * a.n_const + sym_index_plain(fb, (u64)mm, a.bps)];
+            s_sym[buf][i] = v;
+        }
+    };
+    __syncthreads();
+    if (f0 < f1) stage(0, f0);
+    __syncthreads();
+
+    int buf = 0;
+    for (u64 f = f0; f < f1; ++f, buf ^= 1) {
+        if (f + 1 < f1) stage(buf ^ 1, f + 1); /* overlap next frame's symbol fetch */
+        f32x2 win[J]; /* (i, q) of symbol m - j as one packed pair */
+#pragma unroll
+        for (int j = 0; j < J; ++j) win[j] = reinterpret_cast<const f32x2*>(s_sym[buf])[tid + HALO - j];
+
+        float4* wout = s_out[wid];
+#pragma unroll
+        for (int pp = 0; pp < SPS; pp += 2) {
+            float2 o[2];
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int p = pp + e;
+                f32x2 acc = 0ull; /* (+0.0f, +0.0f) */
+#pragma unroll
+                for (int j = 0; j < J; ++j) {
+                    if (p + j * SPS < NT)
+                        acc = mac2<FMA>(acc, win[j], pk2(taps.hh[p + j * SPS].x, taps.hh[p + j * SPS].y), one);
+                }
+                const float2 bb = unpk2(acc);
+                o[e] = mix_iq(bb.x, bb.y, cs[p], sn[p]);
+            }
+            /* chunk c = pp/2 of row `lane` (4 chunks of 16 B per row), XOR-swizzled */
+            const int c = pp >> 1;
+            wout[lane * 4 + (c ^ ((lane >> 1) & 3))] = make_float4(o[0].x, o[0].y, o[1].x, o[1].y);
+        }
+        __syncwarp();
+        /* coalesced write-out of this warp's 32 symbols = 256 samples = 128 float4 */
+        const u64 sym_w0 = k0 + (u64)wid * 32;
+        float4* gout = reinterpret_cast<float4*>(a.tx + f * a.L + sym_w0 * SPS);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int g = lane + 32 * i; /* linear 16-byte chunk in the warp tile */
+            const int row = g >> 2, c = g & 3;
+            float4 v = wout[row * 4 + (c ^ ((row >> 1) & 3))];
+            if (sym_w0 + row < a.nsym) __stcs(gout + g, v);
+        }
+        __syncthreads(); /* s_sym[buf^1] staged, s_out reusable */
+    }
+}
+
+/* ------------------------------------------------------------------ launchers */
+bool tx_rect_fast_supported(uint32_t bps) { return bps == 1 || bps == 2 || bps == 4 || bps == 8; }
+uint64_t tx_rect_fast_tiles(uint64_t L) { return (L + 4 * kThreads - 1) / (4 * kThreads); }
+cudaError_t tx_rect_fast_launch(const TxArgs& a, cudaStream_t stream)
+{
+    dim3 grid((unsigned)tx_rect_fast_tiles(a.L), (unsigned)((a.F + a.frames_per_block - 1) / a.frames_per_block));
+    switch (a.bps) {
+    case 1: tx_rect_fast_kernel<1><<<grid, kThreads, 0, stream>>>(a); break;
+    case 2: tx_rect_fast_kernel<2><<<grid, kThreads, 0, stream>>>(a); break;
+    case 4: tx_rect_fast_kernel<4><<<grid, kThreads, 0, stream>>>(a); break;
+    default: tx_rect_fast_kernel<8><<<grid, kThreads, 0, stream>>>(a); break;
+    }
+    return cudaGetLastError();
+}
+
+bool tx_shaped_fast_supported(uint32_t sps, uint32_t n_taps) { return sps == 8 && n_taps == 129; }
+uint64_t tx_shaped_fast_tiles(uint64_t nsym) { return (nsym + kThreads - 1) / kThreads; }
+cudaError_t tx_shaped_fast_launch(const TxArgs& a, const float* h_taps, bool fma, cudaStream_t stream)
+{
+    dim3 grid((unsigned)tx_shaped_fast_tiles(a.nsym), (unsigned)((a.F + a.frames_per_block - 1) / a.frames_per_block));
+    const TapsParam<129> tp = make_taps_param<129>(h_taps);
+    if (fma) tx_shaped_fast_kernel<8, 129, true><<<grid, kThreads, 0, stream>>>(a, tp);
+    else tx_shaped_fast_kernel<8, 129, false><<<grid, kThreads, 0, stream>>>(a, tp);
+    return cudaGetLastError();
+}
+
+} /* namespace mg */
