@@ -10,5 +10,7 @@ sm_100 GPU every compute call raises.
 from .capi import (ModemError, Modem, ModemCfg, lib, build_library, library_path, host_constellation,
                    lowpass_taps, rrc_taps, sample_freq, samples_per_symbol, FLAG_FUSED_MAC)
 
-__all__ = ["ModemError", "Modem", "ModemCfg", "lib", "build_library", "library_path", "host_constellation",
+from .sharding import shard_range, shard_channels
+
+__all__ = ["shard_range", "shard_channels", "ModemError", "Modem", "ModemCfg", "lib", "build_library", "library_path", "host_constellation",
            "lowpass_taps", "rrc_taps", "sample_freq", "samples_per_symbol", "FLAG_FUSED_MAC"]

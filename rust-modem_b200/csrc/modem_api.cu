@@ -44,9 +44,19 @@ struct modem_ctx {
     size_t n_channels = 0, frames_per_channel = 1;
     u64* d_counters = nullptr;
     Scratch s_bits, s_tx, s_iq, s_rx, s_sym, s_bits_out, s_soft, s_filt;
+    /* host-buffer loopback pipeline: three lanes, each with its own stream and chunk buffers */
+    struct Lane {
+        cudaStream_t s = nullptr;
+        cudaEvent_t done = nullptr;
+        Scratch bits, tx, sym, out;
+    } lanes[3];
+    bool lanes_ready = false;
+    cudaEvent_t ev_start = nullptr;
+    u64 frame_base = 0; /* see ChannelView::frame_base */
     uint64_t launches = 0;
     bool force_generic = false;
     int rx_variant = 0; /* MODEM_GPU_RX_VARIANT: tuning knob, 0 = default */
+    size_t pipe_chunk = 0; /* MODEM_GPU_PIPE_CHUNK: frames per pipeline chunk (0 = ~64 MB of TX samples) */
     std::string last_error;
 };
 
@@ -153,6 +163,7 @@ mg::ChannelView channel_view(const modem_ctx* ctx)
     v.w0 = ctx->cfg.sample_freq;
     v.po0 = ctx->cfg.phase_offset;
     v.frames_per_channel = ctx->n_channels ? ctx->frames_per_channel : 1;
+    v.frame_base = ctx->frame_base;
     return v;
 }
 
@@ -167,7 +178,7 @@ uint32_t frames_per_block(const modem_ctx* ctx, u64 F, u64 tiles_x)
     if (ctx->n_channels) {
         u64 fc = ctx->frames_per_channel;
         if (fpb > fc) fpb = fc;
-        while (fc % fpb) --fpb;
+        while (fc % fpb || ctx->frame_base % fpb) --fpb; /* a CTA's frames must share one carrier */
     }
     return (uint32_t)fpb;
 }
@@ -431,6 +442,8 @@ int modem_gpu_create(modem_ctx_t** out, int device, const modem_cfg_t* cfg)
     ctx->force_generic = fg && fg[0] == '1';
     const char* rv = getenv("MODEM_GPU_RX_VARIANT");
     ctx->rx_variant = rv ? atoi(rv) : 0;
+    const char* pc = getenv("MODEM_GPU_PIPE_CHUNK");
+    ctx->pipe_chunk = pc ? (size_t)atoll(pc) : 0;
 
     rc = MODEM_OK;
     cudaError_t e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
@@ -463,6 +476,14 @@ void modem_gpu_destroy(modem_ctx_t* ctx)
                     ctx->s_bits.p, ctx->s_tx.p, ctx->s_iq.p, ctx->s_rx.p, ctx->s_sym.p, ctx->s_bits_out.p, ctx->s_soft.p, ctx->s_filt.p};
     for (void* p : ptrs)
         if (p) cudaFree(p);
+    for (auto& ln : ctx->lanes) {
+        if (ln.s) cudaStreamSynchronize(ln.s);
+        for (void* p : {ln.bits.p, ln.tx.p, ln.sym.p, ln.out.p})
+            if (p) cudaFree(p);
+        if (ln.done) cudaEventDestroy(ln.done);
+        if (ln.s) cudaStreamDestroy(ln.s);
+    }
+    if (ctx->ev_start) cudaEventDestroy(ctx->ev_start);
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     cudaGetLastError();
     delete ctx;
@@ -612,6 +633,85 @@ int modem_gpu_demodulate_count(modem_ctx_t* ctx, const modem_c32_t* rx, size_t F
                      seed, frame0);
 }
 
+} /* extern "C" */
+
+namespace {
+/*
+ * Host-buffer loopback, pipelined: the frames are cut into chunks that go round three lanes;
+ * each lane runs H2D(bits) -> TX kernel -> RX kernel -> D2H(sym, bits) on its own stream, so
+ * one lane's copies (two independent DMA directions) overlap another lane's kernels.  The
+ * chunk's TX samples live in a lane scratch buffer of at most ~64 MB, which mostly stays in
+ * the 126 MB L2 between the TX and the RX kernel.
+ */
+int loopback_pipelined(modem_ctx* ctx, const uint8_t* bits, size_t F, size_t nbits, float sigma, uint64_t seed,
+                       uint64_t frame0, uint8_t* sym, uint8_t* bits_out, uint64_t counters[2], size_t Fc)
+{
+    const size_t L = modem_gpu_frame_samples(ctx, nbits);
+    const size_t K = modem_gpu_decided_symbols(ctx, L);
+    const size_t bps = ctx->cfg.bits_per_symbol;
+    if (!ctx->lanes_ready) {
+        for (auto& ln : ctx->lanes) {
+            CK(ctx, cudaStreamCreateWithFlags(&ln.s, cudaStreamNonBlocking));
+            CK(ctx, cudaEventCreateWithFlags(&ln.done, cudaEventDisableTiming));
+        }
+        CK(ctx, cudaEventCreateWithFlags(&ctx->ev_start, cudaEventDisableTiming));
+        ctx->lanes_ready = true;
+    }
+    CK(ctx, cudaMemsetAsync(ctx->d_counters, 0, 2 * sizeof(u64), ctx->stream));
+    CK(ctx, cudaEventRecord(ctx->ev_start, ctx->stream));
+    for (auto& ln : ctx->lanes) CK(ctx, cudaStreamWaitEvent(ln.s, ctx->ev_start, 0));
+
+    cudaStream_t user_stream = ctx->stream;
+    int rc = MODEM_OK;
+    size_t c = 0;
+    for (size_t fs = 0; fs < F && !rc; fs += Fc, ++c) {
+        const size_t n = std::min(Fc, F - fs);
+        auto& ln = ctx->lanes[c % 3];
+        rc = ensure(ctx, ln.bits, Fc * nbits);
+        if (!rc) rc = ensure(ctx, ln.tx, Fc * L * sizeof(float2));
+        if (!rc && sym) rc = ensure(ctx, ln.sym, Fc * K);
+        if (!rc && bits_out) rc = ensure(ctx, ln.out, Fc * K * bps);
+        if (rc) break;
+        ctx->stream = ln.s; /* launch_* enqueue on ctx->stream */
+        ctx->frame_base = fs;
+        cudaError_t e = cudaMemcpyAsync(ln.bits.p, bits + fs * nbits, n * nbits, cudaMemcpyHostToDevice, ln.s);
+        if (e == cudaSuccess) {
+            rc = launch_tx(ctx, (const uint8_t*)ln.bits.p, n, nbits, (float2*)ln.tx.p, nullptr);
+            if (!rc)
+                rc = launch_rx(ctx, (const float2*)ln.tx.p, n, L, sym ? (uint8_t*)ln.sym.p : nullptr,
+                               bits_out ? (uint8_t*)ln.out.p : nullptr, nullptr, nullptr, (const uint8_t*)ln.bits.p, nbits,
+                               ctx->d_counters, sigma, seed, frame0 + fs);
+            if (!rc && sym && K) e = cudaMemcpyAsync(sym + fs * K, ln.sym.p, n * K, cudaMemcpyDeviceToHost, ln.s);
+            if (!rc && e == cudaSuccess && bits_out && K)
+                e = cudaMemcpyAsync(bits_out + fs * K * bps, ln.out.p, n * K * bps, cudaMemcpyDeviceToHost, ln.s);
+        }
+        ctx->stream = user_stream;
+        ctx->frame_base = 0;
+        if (e != cudaSuccess) rc = fail(ctx, MODEM_ERR_CUDA, std::string("loopback pipeline: ") + cudaGetErrorString(e));
+    }
+    ctx->stream = user_stream;
+    ctx->frame_base = 0;
+    for (auto& ln : ctx->lanes) {
+        CK(ctx, cudaEventRecord(ln.done, ln.s));
+        CK(ctx, cudaStreamWaitEvent(user_stream, ln.done, 0));
+    }
+    if (rc) {
+        cudaStreamSynchronize(user_stream);
+        return rc;
+    }
+    u64 h[2] = {0, 0};
+    CK(ctx, cudaMemcpyAsync(h, ctx->d_counters, sizeof h, cudaMemcpyDeviceToHost, user_stream));
+    CK(ctx, cudaStreamSynchronize(user_stream));
+    if (counters) {
+        counters[0] += h[0];
+        counters[1] += h[1];
+    }
+    return MODEM_OK;
+}
+} // namespace
+
+extern "C" {
+
 int modem_gpu_loopback(modem_ctx_t* ctx, const uint8_t* bits, size_t F, size_t nbits, float sigma, uint64_t seed,
                        uint64_t frame0, modem_c32_t* tx, uint8_t* sym, uint8_t* bits_out, uint64_t counters[2])
 {
@@ -622,6 +722,16 @@ int modem_gpu_loopback(modem_ctx_t* ctx, const uint8_t* bits, size_t F, size_t n
     const size_t L = modem_gpu_frame_samples(ctx, nbits);
     const size_t K = modem_gpu_decided_symbols(ctx, L);
     const size_t bps = ctx->cfg.bits_per_symbol;
+    if (!tx && L && !is_device_ptr(bits) && !is_device_ptr(sym) && !is_device_ptr(bits_out)) {
+        /* host buffers and no TX dump requested: chunked three-lane pipeline */
+        size_t Fc = ctx->pipe_chunk ? ctx->pipe_chunk : std::max<size_t>(1, ((size_t)64 << 20) / (L * sizeof(float2)));
+        if (ctx->n_channels) { /* chunk boundaries on channel boundaries (or whole divisors of them) */
+            const size_t fc = ctx->frames_per_channel;
+            if (Fc >= fc) Fc -= Fc % fc;
+            else while (fc % Fc) --Fc;
+        }
+        if (F > Fc) return loopback_pipelined(ctx, bits, F, nbits, sigma, seed, frame0, sym, bits_out, counters, Fc);
+    }
     Staged sb, st, ss, so;
     int rc = stage_in(ctx, ctx->s_bits, bits, F * nbits, &sb);
     if (rc) return rc;

@@ -267,6 +267,33 @@ def test_device_pointers_torch(pkg, orc):
     assert (err, cmp_) == (0, K * 2 * F)
 
 
+@pytest.mark.parametrize("chunk", [3, 4, 7])
+def test_host_loopback_pipeline(pkg, orc, chunk, monkeypatch):
+    """Host-buffer loopback runs as a chunked three-lane pipeline (H2D | kernels | D2H): same results,
+    including a multi-carrier bank whose channels straddle chunks and noise indexed by global frame id."""
+    monkeypatch.setenv("MODEM_GPU_PIPE_CHUNK", str(chunk))
+    kw = path_kwargs("qpsk", sps=8)
+    m, o = make(pkg, orc, **kw)
+    bits = rand_bits(91, 26, 2 * 700)
+    sigma = o.sigma_for_ebn0(5.0)
+    sym_ref, bits_ref, cnt_ref = o.loopback(bits, sigma=sigma, seed=5, frame0=40, threads=4)
+    out = m.loopback(bits, sigma=sigma, seed=5, frame0=40)
+    assert np.array_equal(out["sym"], sym_ref) and np.array_equal(out["bits"], bits_ref)
+    assert (out["errors"], out["compared"]) == cnt_ref
+    # bank: 6 channels x 4 frames, chunk sizes that do not divide the channel size
+    hz = [1100 + 333 * c for c in range(6)]  # 2*f_c stays in the low-pass stop band: error-free
+    mb = pkg.Modem(**kw)
+    mb.set_channels([pkg.sample_freq(h, 10000) for h in hz], 4)
+    bits2 = rand_bits(92, 24, 2 * 600)
+    got = mb.loopback(bits2)
+    for c in range(6):
+        oc = orc.OraclePath(**dict(kw, carrier_hz=hz[c]))
+        s_ref, b_ref, _ = oc.loopback(bits2[4 * c: 4 * c + 4])
+        assert np.array_equal(got["sym"][4 * c: 4 * c + 4], s_ref), f"channel {c}"
+        assert np.array_equal(got["bits"][4 * c: 4 * c + 4], b_ref)
+    assert got["errors"] == 0 and got["compared"] == got["bits"].size
+
+
 def test_empty_and_degenerate_inputs(pkg, orc):
     kw = path_kwargs("qpsk", sps=8)
     m, o = make(pkg, orc, **kw)
