@@ -1,0 +1,51 @@
+// build.rs -- compiles the CUDA library for sm_100a with nvcc and links it statically.
+//
+// NOT COMPILED IN THIS REPOSITORY'S CI: the development image has no Rust toolchain.  The same
+// objects are built by rust-modem_b200/csrc/Makefile and exercised through the identical
+// extern "C" symbols by the C++ mirror (rust-modem_b200/host) and the Python tests.
+//
+// Drop this file next to the reference's Cargo.toml and add `build = "build.rs"` to [package].
+use std::env;
+use std::path::PathBuf;
+use std::process::Command;
+
+fn main() {
+    let out = PathBuf::from(env::var("OUT_DIR").unwrap());
+    let csrc = PathBuf::from(env::var("MODEM_GPU_CSRC").unwrap_or_else(|_| "rust-modem_b200/csrc".into()));
+    let cuda = env::var("CUDA_HOME").unwrap_or_else(|_| "/usr/local/cuda".into());
+    let nvcc = format!("{}/bin/nvcc", cuda);
+    let units = ["modem_api.cu", "tx_fast.cu", "rx_fast_64.cu", "rx_fast_129.cu", "rx_ws_64.cu", "rx_fast_dispatch.cu"];
+    let mut objs = Vec::new();
+    for u in units.iter() {
+        let o = out.join(u.replace(".cu", ".o"));
+        let st = Command::new(&nvcc)
+            .args(["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo", "-fmad=false"])
+            .args(["-Xcompiler", "-fPIC", "-Xcompiler", "-ffp-contract=off"])
+            .args(["-DRX_DEFAULT_THREADS=128", "-DRX_DEFAULT_MINB=5", "-DRX_DEFAULT_R=2", "-DRX_DEFAULT_PF=3"])
+            .arg("-c").arg("-o").arg(&o).arg(csrc.join(u))
+            .status().expect("nvcc not found");
+        assert!(st.success(), "nvcc failed on {}", u);
+        objs.push(o);
+    }
+    // host-side tables: the reference's mapper formulas, unfused binary32
+    let ht = out.join("host_tables.o");
+    let st = Command::new("g++")
+        .args(["-O2", "-std=c++17", "-fPIC", "-ffp-contract=off", "-c", "-o"]).arg(&ht)
+        .arg(csrc.join("host_tables.cpp")).status().expect("g++ not found");
+    assert!(st.success());
+    objs.push(ht);
+    let lib = out.join("libmodem_gpu.a");
+    let st = Command::new("ar").arg("rcs").arg(&lib).args(&objs).status().unwrap();
+    assert!(st.success());
+
+    println!("cargo:rustc-link-search=native={}", out.display());
+    println!("cargo:rustc-link-lib=static=modem_gpu");
+    println!("cargo:rustc-link-search=native={}/lib64", cuda);
+    println!("cargo:rustc-link-lib=static=cudart_static");
+    println!("cargo:rustc-link-lib=dylib=stdc++");
+    println!("cargo:rustc-link-lib=dylib=dl");
+    println!("cargo:rustc-link-lib=dylib=rt");
+    println!("cargo:rustc-link-lib=dylib=pthread");
+    // NCCL is dlopen()ed by the library at the first modem_gpu_comm_* call: no link-time dependency.
+    println!("cargo:rerun-if-changed={}", csrc.display());
+}

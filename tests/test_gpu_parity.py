@@ -165,6 +165,21 @@ def test_rx_phase_offset_and_sample0(pkg, orc):
     _rx_check(m, o, o.modulate(bits), "phase_offset")
 
 
+def test_parity_across_2p24(pkg, orc):
+    """Reference quirk: the NCO evaluates `s as f32` (carrier.rs:18), so past 2^24 samples the counter is
+    quantised, the double-frequency term stops being a clean tone and the reference's own round trip makes
+    bit errors.  The GPU path must reproduce that exactly, not "fix" it."""
+    kw = path_kwargs("qpsk", sps=8, sample0=(1 << 24) - 3000)
+    m, o = make(pkg, orc, **kw)
+    bits = rand_bits(46, 3, 2 * 4096)
+    tx_ref = o.modulate(bits)
+    assert_buffers(m.modulate(bits), tx_ref, "tx across 2^24")
+    out, sym_ref, bits_ref = _rx_check(m, o, tx_ref, "rx across 2^24")
+    lb = m.loopback(bits)
+    K = sym_ref.shape[1]
+    assert lb["errors"] == int((bits_ref != bits[:, : 2 * K]).sum())
+
+
 def test_rx_arbitrary_input(pkg, orc):
     """The demodulator on an arbitrary complex stream (not produced by our TX): only .re is read."""
     kw = path_kwargs("qpsk", sps=8)
