@@ -171,6 +171,15 @@ int modem_gpu_demodulate_count(modem_ctx_t* ctx, const modem_c32_t* rx, size_t F
                                uint8_t* sym, uint8_t* bits, const uint8_t* ref_bits, size_t ref_stride,
                                uint64_t* counters, float sigma, uint64_t seed, uint64_t frame0);
 
+/* loopback_device: the whole loopback, stream-ordered and device-resident (nothing is synchronised):
+ * bits / tx (nullable => context scratch) / sym / bits_out (nullable) are device pointers, counters is
+ * a DEVICE u64[2] that is accumulated into.  Internally the frames are cut into chunks of ~48 MB of
+ * TX samples and the TX kernel of chunk c+1 runs on the context's stream while the RX kernel of chunk
+ * c runs on a helper stream: the RX reads its chunk out of the 126 MB L2 instead of HBM. */
+int modem_gpu_loopback_device(modem_ctx_t* ctx, const uint8_t* bits, size_t F, size_t nbits,
+                              float sigma, uint64_t seed, uint64_t frame0, modem_c32_t* tx,
+                              uint8_t* sym, uint8_t* bits_out, uint64_t* counters);
+
 /* loopback: modulate -> (AWGN) -> demodulate -> count bit errors against the input bits
  * over the decided symbols.  tx (nullable => context scratch) receives the clean TX
  * samples.  counters[0] += bit errors, counters[1] += bits compared (host pointer,

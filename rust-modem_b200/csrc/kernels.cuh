@@ -152,6 +152,28 @@ __global__ void __launch_bounds__(kThreads) tx_shaped_generic_kernel(const __gri
     }
 }
 
+/* NCO table: row c = pad_lo zeros, then (cos t, sin t) for n = 0..len-1, t = mod_trig(w_c * (sample0 + n) as f32)
+ * (+ po_c if with_po), then pad_hi zeros.  carrier.rs:17-26 + util.rs:3-6 evaluated once per (channel, sample
+ * index) instead of per frame; the zero margins stand for "no sample there" (zero FIR history, fir.rs:13). */
+__global__ void __launch_bounds__(kThreads)
+    carrier_table_kernel(float2* out, u64 len, u64 pad_lo, u64 pad_hi, u64 ch0, u64 nch, ChannelView ch, u64 sample0, int with_po)
+{
+    const u64 row = pad_lo + len + pad_hi, total = nch * row;
+    for (u64 g = (u64)blockIdx.x * kThreads + threadIdx.x; g < total; g += (u64)gridDim.x * kThreads) {
+        const u64 c = g / row, j = g % row;
+        float2 v = make_float2(0.0f, 0.0f);
+        if (j >= pad_lo && j < pad_lo + len) {
+            const u64 n = j - pad_lo;
+            const float w = ch.w ? __ldg(ch.w + ch0 + c) : ch.w0;
+            const float po = with_po ? (ch.po ? __ldg(ch.po + ch0 + c) : ch.po0) : 0.0f;
+            float sn, cs;
+            mg_sincosf(__fadd_rn(nco_phase(w, sample0 + n), po), &sn, &cs);
+            v = make_float2(cs, sn);
+        }
+        out[g] = v;
+    }
+}
+
 /* ================================================================== AWGN ========== */
 /* In place: buf[f][n] += sigma * (n0 + j n1).  One thread = one Philox call = 2 samples. */
 __global__ void __launch_bounds__(kThreads) awgn_kernel(float2* buf, u64 F, u64 L, Noise nz)

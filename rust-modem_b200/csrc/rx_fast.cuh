@@ -43,8 +43,7 @@ struct RxFastCfg {
     static constexpr int ITER = (NCHUNK + THREADS - 1) / THREADS;
     static constexpr int NSTEP = NB + R - 1;      /* blocks one thread walks */
     static constexpr size_t SMEM_V = sizeof(float4) * PCHUNK;
-    static constexpr size_t SMEM_CS = sizeof(float4) * NCHUNK;
-    static size_t smem(uint32_t lut_entries) { return SMEM_V + SMEM_CS + sizeof(float2) * lut_entries; }
+    static size_t smem(uint32_t lut_entries) { return SMEM_V + sizeof(float2) * lut_entries; }
     static_assert(THREADS % PADW == 0, "phase A position arithmetic needs THREADS % (4R) == 0");
 };
 
@@ -79,32 +78,22 @@ __global__ void __launch_bounds__(THREADS, MINB)
     using C = RxFastCfg<NT, OFF, THREADS, R>;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float4* s_v = reinterpret_cast<float4*>(smem_raw); /* padded chunks of (vi0,vq0,vi1,vq1) */
-    float4* s_cs = s_v + C::PCHUNK;                     /* per chunk: (c0,-s0,c1,-s1) */
-    float2* s_slut = reinterpret_cast<float2*>(s_cs + C::NCHUNK);
+    float2* s_slut = reinterpret_cast<float2*>(s_v + C::PCHUNK);
 
     const int tid = threadIdx.x;
     for (uint32_t i = tid; i < a.n_tables * a.n_const; i += THREADS) s_slut[i] = a.slut[i];
 
     const u64 f0 = (u64)blockIdx.y * a.frames_per_block;
     const u64 f1 = min(a.F, f0 + a.frames_per_block);
-    const float w = chan_w(a.ch, f0), po = chan_po(a.ch, f0);
     const u64 k0 = (u64)blockIdx.x * C::TS;
     /* sample index of tile-local j = 0; even by the choice of OFF */
     const long long nbase = (long long)(k0 * 8 + a.delay) + OFF - 8 * C::NB + 1;
     const bool interior = nbase >= 0 && (u64)(nbase + C::NSAMP) <= a.L;
 
-    for (int q = tid; q < C::NCHUNK; q += THREADS) {
-        float v[4];
-#pragma unroll
-        for (int e = 0; e < 2; ++e) {
-            long long n = nbase + 2 * q + e;
-            float s = 0.0f, c = 0.0f;
-            if (n >= 0 && (u64)n < a.L) mg_sincosf(__fadd_rn(nco_phase(w, a.sample0 + (u64)n), po), &s, &c);
-            v[2 * e] = c;
-            v[2 * e + 1] = -s;
-        }
-        s_cs[q] = make_float4(v[0], v[1], v[2], v[3]);
-    }
+    /* NCO values of the tile: read every frame from the zero-padded global table (ChannelView::cs_tab).
+     * The tile's 17 KB slice stays L1/L2-resident across the frame loop, costs no shared memory and no
+     * setup pass; cs4[q] = (cos, sin) of samples nbase+2q, nbase+2q+1 (zero outside the frame). */
+    const float4* cs4 = reinterpret_cast<const float4*>(chan_table(a.ch, f0) + nbase) + tid;
 
     const u64 ka = k0 + (u64)R * tid; /* this thread's symbols: ka .. ka+R-1 */
     uint32_t toff[R];
@@ -152,7 +141,7 @@ __global__ void __launch_bounds__(THREADS, MINB)
     };
     if (PF == 2 && f0 < f1) load_tile(frame);
     for (u64 f = f0; f < f1; ++f, orow += a.K, frame += a.L) {
-        __syncthreads(); /* previous frame's phase B finished; s_cs / s_slut visible */
+        __syncthreads(); /* previous frame's phase B finished; s_slut visible */
         /* ---- phase A: load the tile (all loads issued before the first use), mix, stage */
         if (PF != 2) load_tile(frame);
         if (NOISE) {
@@ -178,11 +167,12 @@ __global__ void __launch_bounds__(THREADS, MINB)
 #pragma unroll
         for (int it = 0; it < C::ITER; ++it) {
             if (it * THREADS + tid < C::NCHUNK) {
-                const float4 cs = s_cs[it * THREADS + tid];
-                /* chunk q = it*THREADS + tid  ->  position q + q/PADW = wbase + it*(THREADS + THREADS/PADW) */
+                const float4 cs = __ldg(cs4 + it * THREADS);
+                /* demodulator.rs:53-54: x*cos, x*(-sin); chunk q = it*THREADS + tid sits at position
+                 * q + q/PADW = wbase + it*(THREADS + THREADS/PADW) */
                 s_v[wbase + it * (THREADS + THREADS / C::PADW)] =
-                    make_float4(__fmul_rn(xr[it][0], cs.x), __fmul_rn(xr[it][0], cs.y), __fmul_rn(xr[it][1], cs.z),
-                                __fmul_rn(xr[it][1], cs.w));
+                    make_float4(__fmul_rn(xr[it][0], cs.x), __fmul_rn(xr[it][0], -cs.y), __fmul_rn(xr[it][1], cs.z),
+                                __fmul_rn(xr[it][1], -cs.w));
             }
         }
         __syncthreads();
@@ -223,22 +213,47 @@ __global__ void __launch_bounds__(THREADS, MINB)
                 }
             };
             load_block(cv, C::NSTEP - 1);
+            /* products run one element AHEAD of their accumulation (pend[] holds fl(v*h) of the previous
+             * element), so an FFMA2 never waits on the FMUL2 issued just before it; per accumulator the
+             * order of additions is unchanged: taps 0..NT-1 */
+            f32x2 pend[R];
+            bool have_pend[R];
+#pragma unroll
+            for (int r = 0; r < R; ++r) have_pend[r] = false;
 #pragma unroll
             for (int s = 0; s < C::NSTEP; ++s) {
                 const int m = C::NSTEP - 1 - s;
                 if (s + 1 < C::NSTEP) load_block(nv, m - 1); /* one block ahead of its use */
 #pragma unroll
                 for (int e = 7; e >= 0; --e) {
+                    f32x2 prod[R];
+                    bool have_prod[R];
 #pragma unroll
                     for (int r = 0; r < R; ++r) {
                         const int b = r - m + C::NB - 1;
                         const int i = 8 * b + 7 - OFF - e; /* tap index, ascending as e descends */
-                        if (b >= 0 && b < C::NB && i >= 0 && i < NT)
-                            acc[r] = mac2<FMA>(acc[r], cv[e], pk2(taps.hh[i].x, taps.hh[i].y), one);
+                        have_prod[r] = b >= 0 && b < C::NB && i >= 0 && i < NT;
+                        if (have_prod[r]) {
+                            if (FMA) acc[r] = fma2(cv[e], pk2(taps.hh[i].x, taps.hh[i].y), acc[r]);
+                            else prod[r] = mul2(cv[e], pk2(taps.hh[i].x, taps.hh[i].y));
+                        }
+                    }
+                    if (!FMA) {
+#pragma unroll
+                        for (int r = 0; r < R; ++r) {
+                            if (have_pend[r]) acc[r] = fma2(acc[r], one, pend[r]);
+                            have_pend[r] = have_prod[r];
+                            if (have_prod[r]) pend[r] = prod[r];
+                        }
                     }
                 }
 #pragma unroll
                 for (int e = 0; e < 8; ++e) cv[e] = nv[e];
+            }
+            if (!FMA) {
+#pragma unroll
+                for (int r = 0; r < R; ++r)
+                    if (have_pend[r]) acc[r] = fma2(acc[r], one, pend[r]);
             }
         }
         float ai[R], aq[R];
@@ -307,10 +322,14 @@ cudaError_t rx_fast_launch_t(const RxArgs& a, const float* h_taps, cudaStream_t 
     const TapsParam<NT> tp = make_taps_param<NT>(h_taps);
     const size_t smem = C::smem(a.n_tables * a.n_const);
     auto kern = rx_fast_kernel<NT, OFF, FMA, NOISE, THREADS, MINB, R, PF>;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    if (e != cudaSuccess) return e;
+    static size_t configured = 0; /* per instantiation: set the attributes once per shared-memory size */
+    if (configured != smem) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        if (e != cudaSuccess) return e;
+        configured = smem;
+    }
     kern<<<grid, THREADS, smem, stream>>>(a, tp);
     return cudaGetLastError();
 }

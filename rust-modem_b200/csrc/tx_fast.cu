@@ -23,6 +23,7 @@ __global__ void __launch_bounds__(kThreads, 4) tx_rect_fast_kernel(const __grid_
     const u64 f0 = (u64)blockIdx.y * a.frames_per_block;
     const u64 f1 = min(a.F, f0 + a.frames_per_block);
     const float w = chan_w(a.ch, f0);
+    const float2* tab = chan_table(a.ch, f0);
 
     uint32_t koff[U]; /* byte offset of the symbol's bits inside a frame row */
     uint32_t noff[U]; /* float4 offset of the sample pair inside a frame row */
@@ -35,8 +36,13 @@ __global__ void __launch_bounds__(kThreads, 4) tx_rect_fast_kernel(const __grid_
         valid[u] = n < a.L;
         noff[u] = pair;
         koff[u] = (uint32_t)(n / a.sps) * BPS;
-        mg_sincosf(nco_phase(w, a.sample0 + n), &s0[u], &c0[u]);
-        mg_sincosf(nco_phase(w, a.sample0 + n + 1), &s1[u], &c1[u]);
+        if (tab && n + 1 < a.L) { /* n is even and the table row is 16-byte aligned */
+            const float4 t = __ldg(reinterpret_cast<const float4*>(tab + n));
+            c0[u] = t.x; s0[u] = t.y; c1[u] = t.z; s1[u] = t.w;
+        } else {
+            mg_sincosf(nco_phase(w, a.sample0 + n), &s0[u], &c0[u]);
+            mg_sincosf(nco_phase(w, a.sample0 + n + 1), &s1[u], &c1[u]);
+        }
     }
 
     const uint8_t* pb = a.bits + f0 * a.nbits;
@@ -104,8 +110,17 @@ __global__ void __launch_bounds__(kThreads)
     const u64 m = k0 + tid;                    /* this thread's symbol */
 
     float cs[SPS], sn[SPS];
+    const float2* tab = chan_table(a.ch, f0);
+    if (tab && (m + 1) * SPS <= a.L) {
 #pragma unroll
-    for (int p = 0; p < SPS; ++p) mg_sincosf(nco_phase(w, a.sample0 + m * SPS + p), &sn[p], &cs[p]);
+        for (int p = 0; p < SPS; p += 2) {
+            const float4 t = __ldg(reinterpret_cast<const float4*>(tab + m * SPS + p));
+            cs[p] = t.x; sn[p] = t.y; cs[p + 1] = t.z; sn[p + 1] = t.w;
+        }
+    } else {
+#pragma unroll
+        for (int p = 0; p < SPS; ++p) mg_sincosf(nco_phase(w, a.sample0 + m * SPS + p), &sn[p], &cs[p]);
+    }
 
     auto stage = [&](int buf, u64 f) {
         const uint8_t* fb = a.bits + f * a.nbits;

@@ -309,6 +309,55 @@ def test_host_loopback_pipeline(pkg, orc, chunk, monkeypatch):
     assert got["errors"] == 0 and got["compared"] == got["bits"].size
 
 
+@pytest.mark.parametrize("chunk,shaped", [(0, False), (5, False), (3, True)])
+def test_device_loopback_pipeline(pkg, orc, chunk, shaped, monkeypatch):
+    """modem_gpu_loopback_device: TX || RX chunk pipeline on two streams with the NCO table; device
+    buffers, stream-ordered, counters accumulated on the device.  Same results as the oracle, with
+    noise indexed by global frame id and a bank whose channels straddle chunks."""
+    import torch
+
+    if chunk:
+        monkeypatch.setenv("MODEM_GPU_LOOP_CHUNK", str(chunk))
+    kw = path_kwargs("qpsk", sps=8, shaped=shaped)
+    m, o = make(pkg, orc, **kw)
+    m.set_stream(torch.cuda.current_stream().cuda_stream)
+    bits = rand_bits(95, 22, 2 * 800)
+    F, nbits = bits.shape
+    L = m.frame_samples(nbits)
+    K = m.decided_symbols(L)
+    sigma = o.sigma_for_ebn0(4.0)
+    sym_ref, bits_ref, cnt_ref = o.loopback(bits, sigma=sigma, seed=11, frame0=3, threads=4)
+    d_bits = torch.from_numpy(bits).cuda()
+    d_tx = torch.empty((F, L, 2), dtype=torch.float32, device="cuda")
+    d_sym = torch.empty((F, K), dtype=torch.uint8, device="cuda")
+    d_out = torch.empty((F, 2 * K), dtype=torch.uint8, device="cuda")
+    d_cnt = torch.zeros(2, dtype=torch.int64, device="cuda")
+    for _ in range(2):  # second pass: cached table, accumulating counters
+        m.loopback_device_into(d_bits, F, nbits, d_cnt, tx=d_tx, sym=d_sym, bits_out=d_out, sigma=sigma, seed=11, frame0=3)
+    torch.cuda.synchronize()
+    assert_buffers(d_tx.cpu().numpy(), o.modulate(bits), "pipelined tx")
+    assert np.array_equal(d_sym.cpu().numpy(), sym_ref) and np.array_equal(d_out.cpu().numpy(), bits_ref)
+    assert tuple(d_cnt.tolist()) == (2 * cnt_ref[0], 2 * cnt_ref[1])
+    # bank with non-zero per-channel phase offsets (separate RX table)
+    hz = [1100 + 333 * c for c in range(4)]
+    po = [0.0, 0.11, -0.2, 0.05]
+    mb = pkg.Modem(**kw)
+    mb.set_stream(torch.cuda.current_stream().cuda_stream)
+    mb.set_channels([pkg.sample_freq(h, 10000) for h in hz], 5, phase_offsets=po)
+    bits2 = rand_bits(96, 20, 2 * 640)
+    d_b2 = torch.from_numpy(bits2).cuda()
+    L2 = mb.frame_samples(bits2.shape[1]); K2 = mb.decided_symbols(L2)
+    d_s2 = torch.empty((20, K2), dtype=torch.uint8, device="cuda")
+    d_c2 = torch.zeros(2, dtype=torch.int64, device="cuda")
+    mb.loopback_device_into(d_b2, 20, bits2.shape[1], d_c2, sym=d_s2)
+    torch.cuda.synchronize()
+    for c in range(4):
+        oc = orc.OraclePath(**dict(kw, carrier_hz=hz[c], phase_offset=po[c]))
+        tx_c = orc.OraclePath(**dict(kw, carrier_hz=hz[c])).modulate(bits2[5 * c: 5 * c + 5])  # TX has no phase offset
+        _, s_ref, _ = oc.demodulate(tx_c, want_filt=False)
+        assert np.array_equal(d_s2[5 * c: 5 * c + 5].cpu().numpy(), s_ref), f"channel {c}"
+
+
 def test_empty_and_degenerate_inputs(pkg, orc):
     kw = path_kwargs("qpsk", sps=8)
     m, o = make(pkg, orc, **kw)
