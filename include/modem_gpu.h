@@ -171,6 +171,17 @@ int modem_gpu_demodulate_count(modem_ctx_t* ctx, const modem_c32_t* rx, size_t F
                                uint8_t* sym, uint8_t* bits, const uint8_t* ref_bits, size_t ref_stride,
                                uint64_t* counters, float sigma, uint64_t seed, uint64_t frame0);
 
+/* ber_sweep (extension, BASELINE config 4): Monte-Carlo BER over n_points noise levels.  The frames are
+ * modulated ONCE into tx (nullable => context scratch); then for every point p the RX kernel re-reads the
+ * clean TX buffer, adds AWGN of sigmas[p] on the fly (Philox stream keyed by seed + p, counter = global
+ * frame id frame0 + f and sample index) and ACCUMULATES {bit errors, bits compared} into the DEVICE array
+ * counters[p][2].  Stream-ordered, device pointers (sigmas is a host array).  Shard frames across ranks by
+ * giving each rank its own bits and frame0, then reduce all points with ONE
+ * modem_gpu_allreduce_counters(comm, counters, 2 * n_points). */
+int modem_gpu_ber_sweep(modem_ctx_t* ctx, const uint8_t* bits, size_t F, size_t nbits, size_t n_points,
+                        const float* sigmas, uint64_t seed, uint64_t frame0, modem_c32_t* tx,
+                        uint64_t* counters);
+
 /* loopback_device: the whole loopback, stream-ordered and device-resident (nothing is synchronised):
  * bits / tx (nullable => context scratch) / sym / bits_out (nullable) are device pointers, counters is
  * a DEVICE u64[2] that is accumulated into.  Internally the frames are cut into chunks of ~48 MB of

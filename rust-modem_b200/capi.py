@@ -88,6 +88,7 @@ def lib():
     L.modem_gpu_awgn.argtypes = [vp, vp, sz, sz, f32, u64, u64]
     L.modem_gpu_demodulate.argtypes = [vp, vp, sz, sz, vp, vp, vp, vp, f32, u64, u64]
     L.modem_gpu_demodulate_count.argtypes = [vp, vp, sz, sz, vp, vp, vp, sz, vp, f32, u64, u64]
+    L.modem_gpu_ber_sweep.argtypes = [vp, vp, sz, sz, sz, f32p, u64, u64, vp, vp]
     L.modem_gpu_loopback_device.argtypes = [vp, vp, sz, sz, f32, u64, u64, vp, vp, vp, vp]
     L.modem_gpu_loopback.argtypes = [vp, u8p, sz, sz, f32, u64, u64, vp, vp, vp, C.POINTER(u64)]
     L.modem_gpu_malloc.argtypes = [vp, C.POINTER(vp), sz]
@@ -263,6 +264,12 @@ class Modem:
         """Stream-ordered: device pointers only, accumulates into device counters u64[2]."""
         self._ck(lib().modem_gpu_demodulate_count(self._ctx, _ptr(rx), F, L, _ptr(sym), _ptr(bits), _ptr(ref_bits),
                                                   ref_stride, _ptr(counters), sigma, seed, frame0))
+
+    def ber_sweep_into(self, bits, F, nbits, sigmas, counters, seed=0, frame0=0, tx=None):
+        """Modulate once, then one noisy RX pass per sigma; device counters [len(sigmas)][2] are accumulated."""
+        sg = np.ascontiguousarray(sigmas, np.float32)
+        self._ck(lib().modem_gpu_ber_sweep(self._ctx, _ptr(bits), F, nbits, len(sg), _f32p(sg), seed, frame0, _ptr(tx),
+                                           _ptr(counters)))
 
     def loopback_device_into(self, bits, F, nbits, counters, tx=None, sym=None, bits_out=None, sigma=0.0, seed=0, frame0=0):
         """Stream-ordered chunked TX||RX pipeline on device buffers; accumulates into device counters u64[2]."""

@@ -809,6 +809,30 @@ int loopback_pipelined(modem_ctx* ctx, const uint8_t* bits, size_t F, size_t nbi
 
 extern "C" {
 
+int modem_gpu_ber_sweep(modem_ctx_t* ctx, const uint8_t* bits, size_t F, size_t nbits, size_t n_points, const float* sigmas,
+                        uint64_t seed, uint64_t frame0, modem_c32_t* tx, uint64_t* counters)
+{
+    if (!ctx || !bits || !counters || (!sigmas && n_points)) return fail(ctx, MODEM_ERR_INVALID, "ber_sweep: null argument");
+    CK(ctx, cudaSetDevice(ctx->device));
+    if (!is_device_ptr(bits) || !is_device_ptr(counters) || (tx && !is_device_ptr(tx)))
+        return fail(ctx, MODEM_ERR_INVALID, "ber_sweep: device pointers required");
+    if (ctx->n_channels && F > ctx->n_channels * ctx->frames_per_channel)
+        return fail(ctx, MODEM_ERR_INVALID, "ber_sweep: more frames than channels * frames_per_channel");
+    const size_t L = modem_gpu_frame_samples(ctx, nbits);
+    if (F == 0 || L == 0 || n_points == 0) return MODEM_OK;
+    float2* d_tx = (float2*)tx;
+    if (!d_tx) {
+        int rc = ensure(ctx, ctx->s_tx, F * L * sizeof(float2));
+        if (rc) return rc;
+        d_tx = (float2*)ctx->s_tx.p;
+    }
+    int rc = launch_tx(ctx, bits, F, nbits, d_tx, nullptr);
+    for (size_t p = 0; p < n_points && !rc; ++p)
+        rc = launch_rx(ctx, d_tx, F, L, nullptr, nullptr, nullptr, nullptr, bits, nbits, (u64*)counters + 2 * p, sigmas[p], seed + p,
+                       frame0);
+    return rc;
+}
+
 int modem_gpu_loopback_device(modem_ctx_t* ctx, const uint8_t* bits, size_t F, size_t nbits, float sigma, uint64_t seed,
                               uint64_t frame0, modem_c32_t* tx, uint8_t* sym, uint8_t* bits_out, uint64_t* counters)
 {

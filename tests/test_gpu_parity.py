@@ -358,6 +358,33 @@ def test_device_loopback_pipeline(pkg, orc, chunk, shaped, monkeypatch):
         assert np.array_equal(d_s2[5 * c: 5 * c + 5].cpu().numpy(), s_ref), f"channel {c}"
 
 
+def test_ber_sweep_matches_oracle(pkg, orc):
+    """BASELINE config 4 in miniature: Eb/N0 sweep, modulate once, per-point counters equal the oracle's
+    (noise key = seed + point, counter = global frame id), and two 'ranks' with disjoint frame ranges add up."""
+    import torch
+
+    kw = path_kwargs("qpsk", sps=8, shaped=True)
+    m, o = make(pkg, orc, **kw)
+    m.set_stream(torch.cuda.current_stream().cuda_stream)
+    bits = rand_bits(97, 12, 2 * 1024)
+    dbs = [0.0, 3.0, 6.0]
+    sig = [o.sigma_for_ebn0(d) for d in dbs]
+    ref = [o.loopback(bits, sigma=s, seed=0xA5A5 + p, frame0=100, threads=4, want_out=False)[2] for p, s in enumerate(sig)]
+    d_bits = torch.from_numpy(bits).cuda()
+    cnt = torch.zeros((3, 2), dtype=torch.int64, device="cuda")
+    m.ber_sweep_into(d_bits, 12, bits.shape[1], sig, cnt, seed=0xA5A5, frame0=100)
+    torch.cuda.synchronize()
+    assert [tuple(r) for r in cnt.tolist()] == ref
+    assert ref[0][0] > ref[1][0] > ref[2][0] > 0
+    # sharded: frames [0,5) and [5,12) with their own frame0, counters summed (what the all-reduce does)
+    c0 = torch.zeros((3, 2), dtype=torch.int64, device="cuda")
+    c1 = torch.zeros((3, 2), dtype=torch.int64, device="cuda")
+    m.ber_sweep_into(d_bits[:5].contiguous(), 5, bits.shape[1], sig, c0, seed=0xA5A5, frame0=100)
+    m.ber_sweep_into(d_bits[5:].contiguous(), 7, bits.shape[1], sig, c1, seed=0xA5A5, frame0=105)
+    torch.cuda.synchronize()
+    assert torch.equal(c0 + c1, cnt)
+
+
 def test_empty_and_degenerate_inputs(pkg, orc):
     kw = path_kwargs("qpsk", sps=8)
     m, o = make(pkg, orc, **kw)
