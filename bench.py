@@ -116,17 +116,35 @@ def run_reference(args, rank):
     v = float(np.mean([x[0] for x in vals]))
     ms = float(np.mean([x[1] for x in vals])) * 1e3
     sample = f"{frames} of {FRAMES} frames x {L} samples per step, {threads} threads (frames sharded)"
-    print(json.dumps({
+    emit({
         "impl": "reference", "metric": "loopback Msamples/s", "value": v, "unit": "Msamples/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "sample": sample},
         "cpu_baseline": {"value": v, "unit": "Msamples/s", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-    }))
+    })
+
+
+_REAL_STDOUT = None
+
+
+def emit(obj):
+    """The ONE JSON line of the contract goes to the process's original stdout; everything else any
+    library prints (e.g. NCCL's version banner at N > 1) has been routed to stderr."""
+    line = (json.dumps(obj) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(line.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, line)
 
 
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)  # fd 1 -> stderr for the rest of the run (C libraries included)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
@@ -296,7 +314,7 @@ def main():
             out["cpu_baseline"] = {"value": v, "unit": "Msamples/s", "cores": threads, "kind": "port",
                                    "sample": f"{frames} of {FRAMES} frames x {L} samples, {dt:.1f} s wall",
                                    "single_thread_value": v1}
-        print(json.dumps(out))
+        emit(out)
     if comm is not None:
         comm.close()
     m.close()

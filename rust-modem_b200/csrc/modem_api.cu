@@ -76,6 +76,7 @@ struct modem_ctx {
     uint64_t launches = 0;
     bool force_generic = false;
     int rx_variant = 0; /* MODEM_GPU_RX_VARIANT: tuning knob, 0 = default */
+    int rx_fpb = 0, rx_tile_major = -1; /* MODEM_GPU_RX_FPB / MODEM_GPU_RX_TILEMAJOR: tuning knobs */
     size_t pipe_chunk = 0; /* MODEM_GPU_PIPE_CHUNK: frames per pipeline chunk (0 = ~64 MB of TX samples) */
     std::string last_error;
 };
@@ -388,6 +389,10 @@ int launch_rx(modem_ctx* ctx, const float2* d_rx, u64 F, u64 L, uint8_t* d_sym, 
                          mg::rx_fast_supported(N);
     if (fast_ok) {
         a.frames_per_block = frames_per_block(ctx, F, mg::rx_fast_tiles(N, a.K, ctx->rx_variant));
+        if (ctx->rx_fpb > 0 && !ctx->n_channels) a.frames_per_block = (uint32_t)std::max<u64>(ctx->rx_fpb, (F + 65534) / 65535);
+        else a.frames_per_block = std::min<uint32_t>(a.frames_per_block, 16); /* measured: 8..16 is the sweet spot once the NCO table removed the per-CTA setup */
+        if (ctx->n_channels) while (ctx->frames_per_channel % a.frames_per_block || ctx->frame_base % a.frames_per_block) --a.frames_per_block;
+        a.tile_major = ctx->rx_tile_major == 0 ? 0u : 1u; /* default on: co-resident CTAs share one NCO table slice in L1 */
         int rc = attach_carrier_table(ctx, a.ch, F, L, true);
         if (rc) return rc;
         if (!a.ch.cs_tab) return fail(ctx, MODEM_ERR_UNSUPPORTED, "carrier bank too large for the NCO table (> 1 GiB)");
@@ -517,6 +522,10 @@ int modem_gpu_create(modem_ctx_t** out, int device, const modem_cfg_t* cfg)
     ctx->force_generic = fg && fg[0] == '1';
     const char* rv = getenv("MODEM_GPU_RX_VARIANT");
     ctx->rx_variant = rv ? atoi(rv) : 0;
+    const char* rf = getenv("MODEM_GPU_RX_FPB");
+    ctx->rx_fpb = rf ? atoi(rf) : 0;
+    const char* tm = getenv("MODEM_GPU_RX_TILEMAJOR");
+    ctx->rx_tile_major = tm ? atoi(tm) : -1;
     const char* pc = getenv("MODEM_GPU_PIPE_CHUNK");
     ctx->pipe_chunk = pc ? (size_t)atoll(pc) : 0;
     const char* lc = getenv("MODEM_GPU_LOOP_CHUNK");

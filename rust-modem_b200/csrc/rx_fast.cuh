@@ -83,12 +83,17 @@ __global__ void __launch_bounds__(THREADS, MINB)
     const int tid = threadIdx.x;
     for (uint32_t i = tid; i < a.n_tables * a.n_const; i += THREADS) s_slut[i] = a.slut[i];
 
-    const u64 f0 = (u64)blockIdx.y * a.frames_per_block;
+    /* tile-major launch order (blockIdx.x = frame group) makes the CTAs that are resident together work on
+     * the same sample tile, so they share its slice of the NCO table in L1 */
+    const u64 f0 = (u64)(a.tile_major ? blockIdx.x : blockIdx.y) * a.frames_per_block;
     const u64 f1 = min(a.F, f0 + a.frames_per_block);
-    const u64 k0 = (u64)blockIdx.x * C::TS;
+    const u64 k0 = (u64)(a.tile_major ? blockIdx.y : blockIdx.x) * C::TS;
     /* sample index of tile-local j = 0; even by the choice of OFF */
     const long long nbase = (long long)(k0 * 8 + a.delay) + OFF - 8 * C::NB + 1;
-    const bool interior = nbase >= 0 && (u64)(nbase + C::NSAMP) <= a.L;
+    /* the sample range of the tile that exists in the frame, [vlo, vhi) as tile-local pair indices: L and
+     * nbase are even, so a 16-byte pair is either entirely inside the frame or entirely outside */
+    const long long vlo_n = nbase < 0 ? 0 : nbase;
+    const long long vhi_n = (u64)(nbase + C::NSAMP) > a.L ? (long long)a.L : nbase + C::NSAMP;
 
     /* NCO values of the tile: read every frame from the zero-padded global table (ChannelView::cs_tab).
      * The tile's 17 KB slice stays L1/L2-resident across the frame loop, costs no shared memory and no
@@ -115,28 +120,23 @@ __global__ void __launch_bounds__(THREADS, MINB)
     u64 orow = f0 * a.K + ka; /* output index of symbol ka in the current frame */
     const uint8_t* refp = a.ref_bits ? a.ref_bits + f0 * a.ref_stride + ka * 2 : nullptr;
     float xr[C::ITER][2]; /* real parts of the tile being staged (PF == 2: of the NEXT frame, in flight during the FIR) */
+    /* which of this thread's chunks exist in the frame: one bit per step, fixed for the whole frame loop, so
+     * the loads below are predicated, never branched around (a branch would make ptxas drain outstanding
+     * loads at the join and defeat any prefetch) */
+    unsigned long long vmask = 0;
+#pragma unroll
+    for (int it = 0; it < C::ITER; ++it) {
+        const long long n = nbase + 2 * (it * THREADS + tid);
+        if (it * THREADS + tid < C::NCHUNK && n >= vlo_n && n < vhi_n) vmask |= 1ull << it;
+    }
     auto load_tile = [&](const float2* fr) {
-        if (interior) {
-            const float4* src = reinterpret_cast<const float4*>(fr + nbase) + tid;
+        const float4* src = reinterpret_cast<const float4*>(fr + nbase) + tid;
 #pragma unroll
-            for (int it = 0; it < C::ITER; ++it) {
-                if (it * THREADS + tid < C::NCHUNK) {
-                    const float4 t = __ldcs(src + it * THREADS);
-                    xr[it][0] = t.x;
-                    xr[it][1] = t.z;
-                }
-            }
-        } else {
-#pragma unroll
-            for (int it = 0; it < C::ITER; ++it) {
-                const long long n = nbase + 2 * (it * THREADS + tid);
-                xr[it][0] = 0.0f;
-                xr[it][1] = 0.0f;
-                if (it * THREADS + tid < C::NCHUNK) {
-                    if (n >= 0 && (u64)n < a.L) xr[it][0] = __ldcs(&fr[n].x);
-                    if (n + 1 >= 0 && (u64)(n + 1) < a.L) xr[it][1] = __ldcs(&fr[n + 1].x);
-                }
-            }
+        for (int it = 0; it < C::ITER; ++it) {
+            float4 t = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+            if ((vmask >> it) & 1ull) t = __ldcs(src + it * THREADS);
+            xr[it][0] = t.x;
+            xr[it][1] = t.z;
         }
     };
     if (PF == 2 && f0 < f1) load_tile(frame);
@@ -151,7 +151,7 @@ __global__ void __launch_bounds__(THREADS, MINB)
                 const long long n = nbase + 2 * (it * THREADS + tid);
                 if (it * THREADS + tid < C::NCHUNK) {
                     float n0 = 0.0f, n1 = 0.0f;
-                    const bool v0 = n >= 0 && (u64)n < a.L, v1 = n + 1 >= 0 && (u64)(n + 1) < a.L;
+                    const bool v0 = n >= vlo_n && n < vhi_n, v1 = v0;
                     if (v0) n0 = noise_re(a.nz, gf, (u64)n);
                     if (v1) n1 = noise_re(a.nz, gf, (u64)(n + 1));
                     /* xr[] must be indexed statically to stay in registers */
@@ -179,14 +179,14 @@ __global__ void __launch_bounds__(THREADS, MINB)
         if (PF == 2 && f + 1 < f1) load_tile(frame + a.L); /* next frame's loads fly during the FIR */
         /* pull the next frame's tile towards L2 while the FIR runs: PF 1 = one prefetch per 128-byte
          * line through the LSU, PF 3 = one bulk (TMA) L2 prefetch of the whole tile by one thread */
-        if (PF == 1 && f + 1 < f1 && interior) {
-            const char* nxt = reinterpret_cast<const char*>(frame + a.L + nbase);
-            for (int o = tid * 128; o < C::NSAMP * 8; o += THREADS * 128)
+        if (PF == 1 && f + 1 < f1) {
+            const char* nxt = reinterpret_cast<const char*>(frame + a.L + vlo_n);
+            for (int o = tid * 128; o < (int)(vhi_n - vlo_n) * 8; o += THREADS * 128)
                 asm volatile("prefetch.global.L2 [%0];" ::"l"(nxt + o));
         }
-        if (PF == 3 && f + 1 < f1 && interior && tid == 0) {
-            const char* nxt = reinterpret_cast<const char*>(frame + a.L + nbase);
-            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(nxt), "r"(C::NSAMP * 8) : "memory");
+        if (PF == 3 && f + 1 < f1 && tid == 0 && vhi_n > vlo_n) {
+            const char* nxt = reinterpret_cast<const char*>(frame + a.L + vlo_n);
+            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(nxt), "r"((int)(vhi_n - vlo_n) * 8) : "memory");
         }
         uint2 refw = make_uint2(0u, 0u);
         if (ref_vec) {
@@ -318,7 +318,8 @@ template <int NT, int OFF, bool FMA, bool NOISE, int THREADS, int MINB, int R, i
 cudaError_t rx_fast_launch_t(const RxArgs& a, const float* h_taps, cudaStream_t stream)
 {
     using C = RxFastCfg<NT, OFF, THREADS, R>;
-    dim3 grid((unsigned)((a.K + C::TS - 1) / C::TS), (unsigned)((a.F + a.frames_per_block - 1) / a.frames_per_block));
+    const unsigned tiles = (unsigned)((a.K + C::TS - 1) / C::TS), groups = (unsigned)((a.F + a.frames_per_block - 1) / a.frames_per_block);
+    dim3 grid = a.tile_major ? dim3(groups, tiles) : dim3(tiles, groups);
     const TapsParam<NT> tp = make_taps_param<NT>(h_taps);
     const size_t smem = C::smem(a.n_tables * a.n_const);
     auto kern = rx_fast_kernel<NT, OFF, FMA, NOISE, THREADS, MINB, R, PF>;
