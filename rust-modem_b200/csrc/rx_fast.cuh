@@ -19,7 +19,7 @@
  *           with its own compile-time tap group, so every accumulator still sees taps
  *           0..NT-1 in order; taps are constant-bank operands.  Shared traffic of the FIR is
  *           (NB+R-1)*64 B per R symbols: 22 B/sample at R = 4, NT = 64;
- *  phase C  slice, pack, count errors; one 32-bit symbol store and one 64-bit bit store.
+ *  phase C  slice, pack, count errors; one R-byte symbol store and one 2R-byte bit store per thread.
  *
  * Shared layout: 16-byte chunk c (samples 2c, 2c+1) lives at chunk position c + c/(4R): one
  * chunk of padding per thread stride, so the 8 lanes of a quarter warp (stride 4R chunks in
@@ -30,6 +30,28 @@
 #include "common.cuh"
 
 namespace mg {
+
+#ifndef MG_RX_LDMODE
+#define MG_RX_LDMODE 3
+#endif
+/* L1 policy of the two per-frame load streams (measured on B200, C2): 0 = 0.583 ms,
+ * x with L1::no_allocate = 0.70-0.71 ms (much worse), see DESIGN.md */
+#if MG_RX_LDMODE == 0
+#define LDX(p) __ldcs(p)
+#define LDC(p) __ldg(p)
+#elif MG_RX_LDMODE == 3
+#define LDX(p) __ldg(p)
+#define LDC(p) __ldg(p)
+#elif MG_RX_LDMODE == 4
+#define LDX(p) __ldcs(p)
+#define LDC(p) ld_keep_f4(p)
+#elif MG_RX_LDMODE == 5
+#define LDX(p) __ldg(p)
+#define LDC(p) ld_keep_f4(p)
+#else
+#define LDX(p) ld_stream_f4(p)
+#define LDC(p) __ldg(p)
+#endif
 
 template <int NT, int OFF, int THREADS, int R>
 struct RxFastCfg {
@@ -134,7 +156,7 @@ __global__ void __launch_bounds__(THREADS, MINB)
 #pragma unroll
         for (int it = 0; it < C::ITER; ++it) {
             float4 t = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-            if ((vmask >> it) & 1ull) t = __ldcs(src + it * THREADS);
+            if ((vmask >> it) & 1ull) t = LDX(src + it * THREADS);
             xr[it][0] = t.x;
             xr[it][1] = t.z;
         }
@@ -167,7 +189,7 @@ __global__ void __launch_bounds__(THREADS, MINB)
 #pragma unroll
         for (int it = 0; it < C::ITER; ++it) {
             if (it * THREADS + tid < C::NCHUNK) {
-                const float4 cs = __ldg(cs4 + it * THREADS);
+                const float4 cs = LDC(cs4 + it * THREADS);
                 /* demodulator.rs:53-54: x*cos, x*(-sin); chunk q = it*THREADS + tid sits at position
                  * q + q/PADW = wbase + it*(THREADS + THREADS/PADW) */
                 s_v[wbase + it * (THREADS + THREADS / C::PADW)] =
@@ -188,10 +210,17 @@ __global__ void __launch_bounds__(THREADS, MINB)
             const char* nxt = reinterpret_cast<const char*>(frame + a.L + vlo_n);
             asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(nxt), "r"((int)(vhi_n - vlo_n) * 8) : "memory");
         }
-        uint2 refw = make_uint2(0u, 0u);
+        uint32_t refw[4] = {0u, 0u, 0u, 0u}; /* 2R reference bits, one byte each */
         if (ref_vec) {
-            if (R == 4) refw = __ldg(reinterpret_cast<const uint2*>(refp));
-            else refw.x = __ldg(reinterpret_cast<const uint32_t*>(refp));
+            if (R == 8) {
+                const uint4 t = __ldg(reinterpret_cast<const uint4*>(refp));
+                refw[0] = t.x; refw[1] = t.y; refw[2] = t.z; refw[3] = t.w;
+            } else if (R == 4) {
+                const uint2 t = __ldg(reinterpret_cast<const uint2*>(refp));
+                refw[0] = t.x; refw[1] = t.y;
+            } else {
+                refw[0] = __ldg(reinterpret_cast<const uint32_t*>(refp));
+            }
         }
 
         /* ---- phase B: one pass over the thread's NB+R-1 blocks, newest first; block m (relative to
@@ -265,19 +294,18 @@ __global__ void __launch_bounds__(THREADS, MINB)
         }
         /* ---- phase C */
         if (vec_out) {
-            uint32_t symw = 0, bitw[2] = {0u, 0u}, nerr = 0;
+            uint32_t symw[2] = {0u, 0u}, bitw[4] = {0u, 0u, 0u, 0u}, nerr = 0;
 #pragma unroll
             for (int r = 0; r < R; ++r) {
                 const float I = __fmul_rn(a.rx_gain, ai[r]), Q = __fmul_rn(a.rx_gain, aq[r]);
                 const uint32_t s = slice_point4(s_slut + toff[r], a.n_const, I, Q);
-                symw |= s << (8 * r);
+                symw[r / 4] |= s << (8 * (r % 4));
                 bitw[r / 2] |= ((s >> 1) | ((s & 1u) << 8)) << (16 * (r % 2));
                 if (a.soft) a.soft[orow + r] = make_float2(I, Q);
                 if (a.ref_bits) {
                     uint32_t ref;
                     if (ref_vec) {
-                        const uint32_t wd = (r / 2) ? refw.y : refw.x;
-                        const uint32_t h = wd >> (16 * (r % 2));
+                        const uint32_t h = refw[r / 2] >> (16 * (r % 2));
                         ref = ((h & 1u) << 1) | ((h >> 8) & 1u);
                     } else {
                         ref = pack_symbol(refp + 2 * r, 2);
@@ -286,11 +314,13 @@ __global__ void __launch_bounds__(THREADS, MINB)
                 }
             }
             if (a.sym) {
-                if (R == 4) *reinterpret_cast<uint32_t*>(a.sym + orow) = symw;
-                else *reinterpret_cast<uint16_t*>(a.sym + orow) = (uint16_t)symw;
+                if (R == 8) *reinterpret_cast<uint2*>(a.sym + orow) = make_uint2(symw[0], symw[1]);
+                else if (R == 4) *reinterpret_cast<uint32_t*>(a.sym + orow) = symw[0];
+                else *reinterpret_cast<uint16_t*>(a.sym + orow) = (uint16_t)symw[0];
             }
             if (a.bits) {
-                if (R == 4) *reinterpret_cast<uint2*>(a.bits + 2 * orow) = make_uint2(bitw[0], bitw[1]);
+                if (R == 8) *reinterpret_cast<uint4*>(a.bits + 2 * orow) = make_uint4(bitw[0], bitw[1], bitw[2], bitw[3]);
+                else if (R == 4) *reinterpret_cast<uint2*>(a.bits + 2 * orow) = make_uint2(bitw[0], bitw[1]);
                 else *reinterpret_cast<uint32_t*>(a.bits + 2 * orow) = bitw[0];
             }
             if (a.ref_bits) {
