@@ -53,6 +53,57 @@ namespace mg {
 #define LDC(p) __ldg(p)
 #endif
 
+/* ---- TMEM as a per-CTA scratchpad for frame-invariant NCO values (TMC > 0) -------------------------
+ * Every thread stages the SAME tile chunks for every frame, so their (cos, sin) never change.  The first
+ * TMC/4 chunks of each thread are parked in tensor memory (one 32-bit column per value, the thread's own
+ * lane) and read back with tcgen05.ld each frame: that traffic bypasses the L1 / shared data pipe, which is
+ * what bounds this kernel.  32 columns per CTA x 12 CTAs per SM fit the 512-column budget. */
+template <int NCOL>
+__device__ __forceinline__ uint32_t tmem_alloc(uint32_t* smem_slot)
+{
+    if ((threadIdx.x >> 5) == 0) { /* one whole warp allocates, then lets other CTAs allocate */
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_slot)), "n"(NCOL) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    return *smem_slot;
+}
+template <int NCOL>
+__device__ __forceinline__ void tmem_free(uint32_t taddr)
+{
+    __syncthreads();
+    if ((threadIdx.x >> 5) == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(NCOL) : "memory");
+}
+/* this warp's lane quarter of the allocation: lane field (bits 31..16) = 32 * (warp % 4) */
+__device__ __forceinline__ uint32_t tmem_warp_addr(uint32_t taddr) { return taddr + ((uint32_t)((threadIdx.x >> 5) & 3) << 21); }
+__device__ __forceinline__ void tmem_st32(uint32_t addr, const float* v)
+{
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,"
+        "%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};" ::"r"(addr),
+        "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7]), "f"(v[8]), "f"(v[9]), "f"(v[10]),
+        "f"(v[11]), "f"(v[12]), "f"(v[13]), "f"(v[14]), "f"(v[15]), "f"(v[16]), "f"(v[17]), "f"(v[18]), "f"(v[19]), "f"(v[20]),
+        "f"(v[21]), "f"(v[22]), "f"(v[23]), "f"(v[24]), "f"(v[25]), "f"(v[26]), "f"(v[27]), "f"(v[28]), "f"(v[29]), "f"(v[30]),
+        "f"(v[31])
+        : "memory");
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t addr, float* v)
+{
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,"
+        "%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7]), "=f"(v[8]), "=f"(v[9]),
+          "=f"(v[10]), "=f"(v[11]), "=f"(v[12]), "=f"(v[13]), "=f"(v[14]), "=f"(v[15]), "=f"(v[16]), "=f"(v[17]), "=f"(v[18]),
+          "=f"(v[19]), "=f"(v[20]), "=f"(v[21]), "=f"(v[22]), "=f"(v[23]), "=f"(v[24]), "=f"(v[25]), "=f"(v[26]), "=f"(v[27]),
+          "=f"(v[28]), "=f"(v[29]), "=f"(v[30]), "=f"(v[31])
+        : "r"(addr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
 template <int NT, int OFF, int THREADS, int R>
 struct RxFastCfg {
     static constexpr int NB = (NT + OFF + 7) / 8; /* blocks that reach one symbol */
@@ -93,7 +144,7 @@ __device__ __forceinline__ uint32_t slice_point4(const float2* t, uint32_t n, fl
     return best;
 }
 
-template <int NT, int OFF, bool FMA, bool NOISE, int THREADS, int MINB, int R, int PF>
+template <int NT, int OFF, bool FMA, bool NOISE, int THREADS, int MINB, int R, int PF, int TMC>
 __global__ void __launch_bounds__(THREADS, MINB)
     rx_fast_kernel(const __grid_constant__ RxArgs a, const __grid_constant__ TapsParam<NT> taps)
 {
@@ -121,6 +172,26 @@ __global__ void __launch_bounds__(THREADS, MINB)
      * The tile's 17 KB slice stays L1/L2-resident across the frame loop, costs no shared memory and no
      * setup pass; cs4[q] = (cos, sin) of samples nbase+2q, nbase+2q+1 (zero outside the frame). */
     const float4* cs4 = reinterpret_cast<const float4*>(chan_table(a.ch, f0) + nbase) + tid;
+    /* TMC columns of tensor memory per thread hold the NCO values of its first TMC/4 chunks */
+    constexpr int TCH = TMC / 4;
+    __shared__ uint32_t s_tmem;
+    uint32_t taddr = 0, twarp = 0;
+    if (TMC > 0) {
+        static_assert(TMC == 0 || TMC == 32 || TMC == 64, "one or two tcgen05 32x32b.x32 transfers per thread");
+        static_assert(TMC == 0 || THREADS <= 128, "a CTA reaches TMEM lanes 32*(warp % 4)");
+        taddr = tmem_alloc<(TMC > 0 ? TMC : 32)>(&s_tmem);
+        twarp = tmem_warp_addr(taddr);
+#pragma unroll
+        for (int h = 0; h < TMC / 32; ++h) {
+            float park[32];
+#pragma unroll
+            for (int it = 0; it < 8; ++it) {
+                const float4 t = __ldg(cs4 + (8 * h + it) * THREADS); /* padded table: always readable */
+                park[4 * it] = t.x; park[4 * it + 1] = t.y; park[4 * it + 2] = t.z; park[4 * it + 3] = t.w;
+            }
+            tmem_st32(twarp + 32 * h, park); /* column field = bits 15..0 */
+        }
+    }
 
     const u64 ka = k0 + (u64)R * tid; /* this thread's symbols: ka .. ka+R-1 */
     uint32_t toff[R];
@@ -186,10 +257,14 @@ __global__ void __launch_bounds__(THREADS, MINB)
                 }
             }
         }
+        float parked[TMC > 0 ? TMC : 4];
+        if (TMC > 0) tmem_ld32(twarp, parked);
+        if (TMC > 32) tmem_ld32(twarp + 32, parked + 32);
 #pragma unroll
         for (int it = 0; it < C::ITER; ++it) {
             if (it * THREADS + tid < C::NCHUNK) {
-                const float4 cs = LDC(cs4 + it * THREADS);
+                const float4 cs = (TMC > 0 && it < TCH) ? make_float4(parked[(4 * it) % (TMC > 0 ? TMC : 4)], parked[(4 * it + 1) % (TMC > 0 ? TMC : 4)], parked[(4 * it + 2) % (TMC > 0 ? TMC : 4)], parked[(4 * it + 3) % (TMC > 0 ? TMC : 4)])
+                                                        : LDC(cs4 + it * THREADS);
                 /* demodulator.rs:53-54: x*cos, x*(-sin); chunk q = it*THREADS + tid sits at position
                  * q + q/PADW = wbase + it*(THREADS + THREADS/PADW) */
                 s_v[wbase + it * (THREADS + THREADS / C::PADW)] =
@@ -341,10 +416,11 @@ __global__ void __launch_bounds__(THREADS, MINB)
         if (refp) refp += a.ref_stride;
     }
     block_count(a, err, cmp);
+    if (TMC > 0) tmem_free<(TMC > 0 ? TMC : 32)>(taddr);
 }
 
 /* ------------------------------------------------------------------ host side */
-template <int NT, int OFF, bool FMA, bool NOISE, int THREADS, int MINB, int R, int PF = RX_DEFAULT_PF>
+template <int NT, int OFF, bool FMA, bool NOISE, int THREADS, int MINB, int R, int PF = RX_DEFAULT_PF, int TMC = RX_DEFAULT_TMC>
 cudaError_t rx_fast_launch_t(const RxArgs& a, const float* h_taps, cudaStream_t stream)
 {
     using C = RxFastCfg<NT, OFF, THREADS, R>;
@@ -352,7 +428,7 @@ cudaError_t rx_fast_launch_t(const RxArgs& a, const float* h_taps, cudaStream_t 
     dim3 grid = a.tile_major ? dim3(groups, tiles) : dim3(tiles, groups);
     const TapsParam<NT> tp = make_taps_param<NT>(h_taps);
     const size_t smem = C::smem(a.n_tables * a.n_const);
-    auto kern = rx_fast_kernel<NT, OFF, FMA, NOISE, THREADS, MINB, R, PF>;
+    auto kern = rx_fast_kernel<NT, OFF, FMA, NOISE, THREADS, MINB, R, PF, TMC>;
     static size_t configured = 0; /* per instantiation: set the attributes once per shared-memory size */
     if (configured != smem) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

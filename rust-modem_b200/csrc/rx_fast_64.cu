@@ -9,9 +9,7 @@ struct V { int threads, r; };
 static V variant_shape(int variant)
 {
     switch (variant) {
-    case 1: case 2: case 3: return {32, 8};
-    case 4: case 5: return {64, 8};
-    case 6: return {32, 4};
+    case 4: case 5: case 6: return {128, 4};
     default: return {64, 4};
     }
 }
@@ -20,12 +18,13 @@ cudaError_t rx_fast_launch_64(const RxArgs& a, const float* h_taps, bool fma, in
     /* tuning variants (MODEM_GPU_RX_VARIANT), headline shape only: odd delay, exact MAC, no noise */
     if (variant && (a.delay & 1u) && !fma && a.nz.sigma == 0.0f) {
         switch (variant) {
-        case 1: return rx_fast_launch_t<64, 0, false, false, 32, 10, 8, 3>(a, h_taps, stream);
-        case 2: return rx_fast_launch_t<64, 0, false, false, 32, 12, 8, 3>(a, h_taps, stream);
-        case 3: return rx_fast_launch_t<64, 0, false, false, 32, 16, 8, 3>(a, h_taps, stream);
-        case 4: return rx_fast_launch_t<64, 0, false, false, 64, 6, 8, 3>(a, h_taps, stream);
-        case 5: return rx_fast_launch_t<64, 0, false, false, 64, 5, 8, 3>(a, h_taps, stream);
-        case 6: return rx_fast_launch_t<64, 0, false, false, 32, 24, 4, 3>(a, h_taps, stream);
+        case 1: return rx_fast_launch_t<64, 0, false, false, 64, 10, 4, 3, 32>(a, h_taps, stream);
+        case 2: return rx_fast_launch_t<64, 0, false, false, 64, 8, 4, 3, 64>(a, h_taps, stream);
+        case 3: return rx_fast_launch_t<64, 0, false, false, 64, 9, 4, 3, 32>(a, h_taps, stream);
+        case 4: return rx_fast_launch_t<64, 0, false, false, 128, 5, 4, 3, 64>(a, h_taps, stream);
+        case 5: return rx_fast_launch_t<64, 0, false, false, 128, 6, 4, 3, 64>(a, h_taps, stream);
+        case 6: return rx_fast_launch_t<64, 0, false, false, 128, 6, 4, 3, 32>(a, h_taps, stream);
+        case 7: return rx_fast_launch_t<64, 0, false, false, 64, 11, 4, 3, 32>(a, h_taps, stream);
         default: break;
         }
     }

@@ -21,7 +21,7 @@ fn main() {
         let st = Command::new(&nvcc)
             .args(["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo", "-fmad=false"])
             .args(["-Xcompiler", "-fPIC", "-Xcompiler", "-ffp-contract=off"])
-            .args(["-DRX_DEFAULT_THREADS=128", "-DRX_DEFAULT_MINB=5", "-DRX_DEFAULT_R=2", "-DRX_DEFAULT_PF=3"])
+            .args(["-DRX_DEFAULT_THREADS=64", "-DRX_DEFAULT_MINB=8", "-DRX_DEFAULT_R=4", "-DRX_DEFAULT_PF=3", "-DRX_DEFAULT_TMC=64"])
             .arg("-c").arg("-o").arg(&o).arg(csrc.join(u))
             .status().expect("nvcc not found");
         assert!(st.success(), "nvcc failed on {}", u);
