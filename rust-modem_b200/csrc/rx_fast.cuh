@@ -144,6 +144,27 @@ __device__ __forceinline__ uint32_t slice_point4(const float2* t, uint32_t n, fl
     return best;
 }
 
+/* the same search for a 4-point table held in registers (QPSK-sized constellations): identical float
+ * operations and tie rule (strict <, lowest index wins), no shared loads, no loop */
+__device__ __forceinline__ uint32_t slice_point_reg4(const float2 (&t)[4], float I, float Q)
+{
+    float d[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const float di = __fsub_rn(I, t[j].x), dq = __fsub_rn(Q, t[j].y);
+        d[j] = __fadd_rn(__fmul_rn(di, di), __fmul_rn(dq, dq));
+    }
+    uint32_t best = 0;
+    float bd = d[0];
+#pragma unroll
+    for (int j = 1; j < 4; ++j)
+        if (d[j] < bd) {
+            bd = d[j];
+            best = j;
+        }
+    return best;
+}
+
 template <int NT, int OFF, bool FMA, bool NOISE, int THREADS, int MINB, int R, int PF, int TMC>
 __global__ void __launch_bounds__(THREADS, MINB)
     rx_fast_kernel(const __grid_constant__ RxArgs a, const __grid_constant__ TapsParam<NT> taps)
@@ -204,6 +225,12 @@ __global__ void __launch_bounds__(THREADS, MINB)
                          ((reinterpret_cast<uintptr_t>(a.bits) % (2 * R)) == 0);
     const bool ref_vec = a.ref_bits && vec_out && (a.ref_stride % (2 * R) == 0) &&
                          ((reinterpret_cast<uintptr_t>(a.ref_bits) % (2 * R)) == 0);
+
+    /* one 4-point table for every symbol: keep it in registers */
+    const bool lut4 = a.n_const == 4 && a.n_tables == 1;
+    float2 rl[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) rl[j] = lut4 ? a.slut[j] : make_float2(0.0f, 0.0f);
 
     uint32_t err = 0, cmp = 0;
     const int wbase = tid + tid / C::PADW;              /* phase A: chunk position of chunk `tid` */
@@ -373,7 +400,7 @@ __global__ void __launch_bounds__(THREADS, MINB)
 #pragma unroll
             for (int r = 0; r < R; ++r) {
                 const float I = __fmul_rn(a.rx_gain, ai[r]), Q = __fmul_rn(a.rx_gain, aq[r]);
-                const uint32_t s = slice_point4(s_slut + toff[r], a.n_const, I, Q);
+                const uint32_t s = lut4 ? slice_point_reg4(rl, I, Q) : slice_point4(s_slut + toff[r], a.n_const, I, Q);
                 symw[r / 4] |= s << (8 * (r % 4));
                 bitw[r / 2] |= ((s >> 1) | ((s & 1u) << 8)) << (16 * (r % 2));
                 if (a.soft) a.soft[orow + r] = make_float2(I, Q);
