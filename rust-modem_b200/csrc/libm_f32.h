@@ -231,4 +231,124 @@ MG_HD float mg_logf_pos(float x)
     return (float)y;
 }
 
+/* ---- atanf / atan2f ---------------------------------------------------------
+ * The reference's PLL takes `(x * carrier.conj()).arg()` (pll.rs:19), i.e. num::Complex::arg =
+ * im.atan2(re) -> libm atan2f.  glibc 2.39 still ships the classic fdlibm binary32 routines for
+ * these two (sysdeps/ieee754/flt-32/{s_atanf,e_atan2f}.c; the correctly-rounded replacements
+ * arrived in 2.41): argument reduction to one of four intervals, an 11-term odd/even split
+ * polynomial, every step a separately rounded binary32 operation (the generic x86-64 build has no
+ * FMA contraction and these two have no ifunc variant).  Restated here with the published
+ * constants; tools/check_libm.c compares against this machine's glibc over every binary32.
+ */
+#if defined(__CUDA_ARCH__)
+#define MG_FMUL(a, b) __fmul_rn((a), (b))
+#define MG_FADD(a, b) __fadd_rn((a), (b))
+#define MG_FSUB(a, b) __fsub_rn((a), (b))
+#define MG_FDIV(a, b) __fdiv_rn((a), (b))
+#else
+static inline float mg_host_fmul(float a, float b) { volatile float r = a * b; return r; }
+#define MG_FMUL(a, b) mg_host_fmul((a), (b)) /* the volatile round-trip forbids host-side fusing */
+#define MG_FADD(a, b) ((a) + (b))
+#define MG_FSUB(a, b) ((a) - (b))
+#define MG_FDIV(a, b) ((a) / (b))
+#endif
+
+MG_HD float mg_atanf(float x)
+{
+    const float hi[4] = {4.6364760399e-01f, 7.8539812565e-01f, 9.8279368877e-01f, 1.5707962513e+00f};
+    const float lo[4] = {5.0121582440e-09f, 3.7748947079e-08f, 3.4473217170e-08f, 7.5497894159e-08f};
+    const float aT0 = 3.3333334327e-01f, aT1 = -2.0000000298e-01f, aT2 = 1.4285714924e-01f, aT3 = -1.1111110449e-01f,
+                aT4 = 9.0908870101e-02f, aT5 = -7.6918758452e-02f, aT6 = 6.6610731184e-02f, aT7 = -5.8335702866e-02f,
+                aT8 = 4.9768779427e-02f, aT9 = -3.6531571299e-02f, aT10 = 1.6285819933e-02f;
+    const uint32_t hx = MG_ASUINT(x), ix = hx & 0x7fffffffu;
+    int id;
+    if (ix >= 0x4c000000u) { /* |x| >= 2^25 */
+        if (ix > 0x7f800000u) return MG_FADD(x, x);
+        const float r = MG_FADD(hi[3], lo[3]);
+        return (hx >> 31) ? -r : r;
+    }
+    if (ix < 0x3ee00000u) { /* |x| < 0.4375 */
+        if (ix < 0x31000000u) return x; /* |x| < 2^-29 */
+        id = -1;
+    } else {
+        x = MG_ASFLOAT(ix);
+        if (ix < 0x3f980000u) { /* |x| < 1.1875 */
+            if (ix < 0x3f300000u) { /* 7/16 <= |x| < 11/16 */
+                id = 0;
+                x = MG_FDIV(MG_FSUB(MG_FMUL(2.0f, x), 1.0f), MG_FADD(2.0f, x));
+            } else {
+                id = 1;
+                x = MG_FDIV(MG_FSUB(x, 1.0f), MG_FADD(x, 1.0f));
+            }
+        } else if (ix < 0x401c0000u) { /* |x| < 2.4375 */
+            id = 2;
+            x = MG_FDIV(MG_FSUB(x, 1.5f), MG_FADD(1.0f, MG_FMUL(1.5f, x)));
+        } else {
+            id = 3;
+            x = MG_FDIV(-1.0f, x);
+        }
+    }
+    const float z = MG_FMUL(x, x);
+    const float w = MG_FMUL(z, z);
+    float s1 = MG_FADD(aT8, MG_FMUL(w, aT10));
+    s1 = MG_FADD(aT6, MG_FMUL(w, s1));
+    s1 = MG_FADD(aT4, MG_FMUL(w, s1));
+    s1 = MG_FADD(aT2, MG_FMUL(w, s1));
+    s1 = MG_FADD(aT0, MG_FMUL(w, s1));
+    s1 = MG_FMUL(z, s1);
+    float s2 = MG_FADD(aT7, MG_FMUL(w, aT9));
+    s2 = MG_FADD(aT5, MG_FMUL(w, s2));
+    s2 = MG_FADD(aT3, MG_FMUL(w, s2));
+    s2 = MG_FADD(aT1, MG_FMUL(w, s2));
+    s2 = MG_FMUL(w, s2);
+    const float t = MG_FMUL(x, MG_FADD(s1, s2));
+    if (id < 0) return MG_FSUB(x, t);
+    const float r = MG_FSUB(hi[id], MG_FSUB(MG_FSUB(t, lo[id]), x));
+    return (hx >> 31) ? -r : r;
+}
+
+MG_HD float mg_atan2f(float y, float x)
+{
+    const float tiny = 1.0e-30f, pi_o_4 = 7.8539818525e-01f, pi_o_2 = 1.5707963705e+00f, pi = 3.1415927410e+00f,
+                pi_lo = -8.7422776573e-08f;
+    const uint32_t hx = MG_ASUINT(x), hy = MG_ASUINT(y);
+    const uint32_t ix = hx & 0x7fffffffu, iy = hy & 0x7fffffffu;
+    if (ix > 0x7f800000u || iy > 0x7f800000u) return MG_FADD(x, y);
+    if (hx == 0x3f800000u) return mg_atanf(y);
+    const uint32_t m = (hy >> 31) | ((hx >> 30) & 2u); /* 2*sign(x) + sign(y) */
+    if (iy == 0) {
+        if (m < 2) return y;
+        return m == 2 ? MG_FADD(pi, tiny) : MG_FSUB(-pi, tiny);
+    }
+    if (ix == 0) return (hy >> 31) ? MG_FSUB(-pi_o_2, tiny) : MG_FADD(pi_o_2, tiny);
+    if (ix == 0x7f800000u) {
+        if (iy == 0x7f800000u) {
+            switch (m) {
+            case 0: return MG_FADD(pi_o_4, tiny);
+            case 1: return MG_FSUB(-pi_o_4, tiny);
+            case 2: return MG_FADD(MG_FMUL(3.0f, pi_o_4), tiny);
+            default: return MG_FSUB(MG_FMUL(-3.0f, pi_o_4), tiny);
+            }
+        }
+        switch (m) {
+        case 0: return 0.0f;
+        case 1: return -0.0f;
+        case 2: return MG_FADD(pi, tiny);
+        default: return MG_FSUB(-pi, tiny);
+        }
+    }
+    if (iy == 0x7f800000u) return (hy >> 31) ? MG_FSUB(-pi_o_2, tiny) : MG_FADD(pi_o_2, tiny);
+    const int k = ((int)iy - (int)ix) >> 23;
+    float z;
+    if (k > 60) z = MG_FADD(pi_o_2, MG_FMUL(0.5f, pi_lo));
+    else if ((hx >> 31) && k < -60) z = 0.0f;
+    else z = mg_atanf(MG_ASFLOAT(MG_ASUINT(MG_FDIV(y, x)) & 0x7fffffffu));
+    switch (m) {
+    case 0: return z;
+    case 1: return MG_ASFLOAT(MG_ASUINT(z) ^ 0x80000000u);
+    case 2: return MG_FSUB(pi, MG_FSUB(z, pi_lo));
+    default: return MG_FSUB(MG_FSUB(z, pi_lo), pi);
+    }
+}
+
 #endif /* MODEM_GPU_LIBM_F32_H */
