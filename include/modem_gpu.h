@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define MODEM_GPU_ABI_VERSION 1
+#define MODEM_GPU_ABI_VERSION 2
 
 enum {
     MODEM_OK = 0,
@@ -112,6 +112,33 @@ int modem_const_apsk(float amplitude, uint32_t bps, const modem_ring_t* rings, s
 int modem_const_by_name(const char* name, float* out_iq, uint32_t* n_tables, uint32_t* evenodd);
 
 const float* modem_lowpass_taps(size_t* n);  /* src/bin/demodulate.rs:82-147, 64 taps */
+const float* modem_hilbert_taps(size_t* n);  /* src/bin/demodulate.rs:48-72, 23 taps */
+
+/* Stateful / time-varying phasors (digital/{bfsk,mfsk,cpfsk,msk,dmpsk}.rs): (i,q) depends on the sample
+ * counter and, for bfsk/mfsk/dmpsk, on a phase carried from symbol to symbol (DigitalPhasor::update).
+ * The phasor sees s = Carrier.sample AFTER the increment of Carrier::next (modulator.rs:86-97), i.e.
+ * s = cfg.sample0 + n + 1 for sample n of a frame; every frame starts from the constructor's state. */
+enum {
+    MODEM_PHASOR_TABLE = 0, /* the memoryless constellation table of modem_cfg_t.const_iq */
+    MODEM_PHASOR_BFSK = 1,  /* bfsk.rs:23-56  */
+    MODEM_PHASOR_MFSK = 2,  /* mfsk.rs:60-84  */
+    MODEM_PHASOR_CPFSK = 3, /* cpfsk.rs:25-44 */
+    MODEM_PHASOR_MSK = 4,   /* msk.rs:21-36 (fed by EvenOddOffset: cfg.q_offset = sps/2, modulate.rs:101-107) */
+    MODEM_PHASOR_DMPSK = 5  /* dmpsk.rs:29-42 */
+};
+typedef struct {
+    uint32_t struct_size;     /* = sizeof(modem_phasor_t) */
+    uint32_t kind;            /* MODEM_PHASOR_* */
+    uint32_t bits_per_symbol; /* must equal cfg.bits_per_symbol */
+    float amplitude;
+    float deviation;          /* bfsk.rs:16, mfsk.rs:52: deviation.sample_freq(); cpfsk.rs:19-20: freq */
+    float phase;              /* dmpsk.rs:20 initial phase */
+    float shift;              /* dmpsk.rs:21 */
+    uint32_t mfsk_increase_map; /* mfsk.rs: 0 = DefaultMap (:22-27), 1 = IncreaseMap (:31-35) */
+} modem_phasor_t;
+/* The stateful `-m` names of src/bin/modulate.rs:74-95 (bfsk, mfsk, msk, 16cpfsk, dqpsk, dbpsk) with that
+ * file's constants.  Returns bps; *evenodd = 1 for msk.  Other names: MODEM_ERR_UNSUPPORTED. */
+int modem_phasor_by_name(const char* name, size_t baud_rate, size_t sample_rate, modem_phasor_t* out, uint32_t* evenodd);
 /* root-raised-cosine, span*sps+1 taps, unit energy (extension) */
 int modem_rrc_taps(float* out, size_t span, size_t sps, double beta);
 /* AWGN sigma that gives the slicer the textbook Eb/N0 (DESIGN.md "AWGN scaling") */
@@ -128,6 +155,9 @@ int modem_gpu_set_stream(modem_ctx_t* ctx, void* cuda_stream);
 int modem_gpu_set_channels(modem_ctx_t* ctx, size_t n_channels, const float* sample_freq,
                            const float* phase_offset, size_t frames_per_channel);
 int modem_gpu_synchronize(modem_ctx_t* ctx);
+/* Replace the table mapper of modem_gpu_modulate* by a stateful phasor (NULL or kind TABLE restores the
+ * table).  TX only: the reference has no receiver for these schemes. */
+int modem_gpu_set_phasor(modem_ctx_t* ctx, const modem_phasor_t* phasor);
 
 size_t modem_gpu_frame_samples(const modem_ctx_t* ctx, size_t nbits);   /* floor(nbits/bps)*sps (data.rs:54-63) */
 size_t modem_gpu_decided_symbols(const modem_ctx_t* ctx, size_t L);     /* floor((L-1-delay-q_offset)/sps)+1 */
@@ -141,6 +171,19 @@ size_t modem_gpu_decided_symbols(const modem_ctx_t* ctx, size_t L);     /* floor
  */
 int modem_gpu_modulate(modem_ctx_t* ctx, const uint8_t* bits, size_t F, size_t nbits,
                        modem_c32_t* tx, modem_c32_t* iq);
+
+/* preamble: the carrier sync tone of modulate.rs:118-126 -- `Modulator::new(&mut carrier,
+ *   Box::new(phasor::Raw::new(amplitude)))` (modulator.rs:8-20,51-62, phasor.rs:5-24) mapped through
+ *   IQSample::modulate: tx [F][n] complex, sample counter from cfg.sample0. */
+int modem_gpu_preamble(modem_ctx_t* ctx, size_t F, size_t n, float amplitude, modem_c32_t* tx);
+
+/* modulate_real: exactly the f32 stream src/bin/modulate.rs writes without --iq (modulate.rs:118-133):
+ *   `preamble` samples of the sync tone (amplitude preamble_amplitude; 0 samples = none), then the data
+ *   samples, each `x.modulate().re`.  The Carrier is shared: its sample counter runs on from the tone into
+ *   the data (modulate.rs:120,128), so data sample n uses Carrier.sample = cfg.sample0 + preamble + n.
+ *   out [F][preamble + L] f32, L = modem_gpu_frame_samples(nbits). */
+int modem_gpu_modulate_real(modem_ctx_t* ctx, const uint8_t* bits, size_t F, size_t nbits, size_t preamble,
+                            float preamble_amplitude, float* out);
 
 /* awgn (extension): buf[f][n] += sigma * N(0,1) per component, Philox4x32-10 keyed by `seed`,
  * counter = (n/2, global frame id frame0+f).  In place. */
@@ -161,6 +204,30 @@ int modem_gpu_awgn(modem_ctx_t* ctx, modem_c32_t* buf, size_t F, size_t L, float
 int modem_gpu_demodulate(modem_ctx_t* ctx, const modem_c32_t* rx, size_t F, size_t L,
                          uint8_t* sym, uint8_t* bits, modem_c32_t* soft, modem_c32_t* filt,
                          float sigma, uint64_t seed, uint64_t frame0);
+
+/* Sample formats of the carrier-recovery front end (src/bin/demodulate.rs:29-34) */
+enum {
+    MODEM_SAMPLES_C32 = 0, /* analytic signal supplied by the caller: num::Complex<f32> per sample */
+    MODEM_SAMPLES_F32 = 1, /* real f32 samples (what modulate writes); analytic = (x, hilbert.add(x)) */
+    MODEM_SAMPLES_I16 = 2  /* real native-endian i16 samples (src/bin/util.rs:3-37), `x as f32` */
+};
+/* lock_phase: Demodulator::lock_phase (demodulator.rs:32-36): for each frame, the first lock_samples
+ *   (LOCK_SAMPLES = 64, demodulator.rs:5) analytic samples drive PLL::handle (pll.rs:16-22) with
+ *   Carrier::next() from cfg.sample0; phase_offset [F] (host or device) receives PLL.phase_offset.
+ *   For real formats the imaginary part is the Hilbert FIR (fir.rs semantics, zero history) of the
+ *   real samples (demodulate.rs:31-34); hilbert_taps == NULL uses modem_hilbert_taps(). */
+int modem_gpu_lock_phase(modem_ctx_t* ctx, const void* samples, uint32_t fmt, size_t F, size_t L,
+                         const float* hilbert_taps, size_t n_hilbert, size_t lock_samples, float* phase_offset);
+
+/* demodulate_real: the whole path of src/bin/demodulate.rs:29-43 per frame: lock_phase over the first
+ *   lock_samples samples (0 = no lock: cfg.phase_offset is used), then Demodulator::next over the remaining
+ *   Lr = L - lock_samples samples with the carrier counter running on (cfg.sample0 + lock_samples + n), the
+ *   frame's own PLL.phase_offset and fresh low-pass history.  Outputs as modem_gpu_demodulate with L := Lr
+ *   (filt [F][Lr] is the `i:{}\tq:{}` stream the binary prints); phase_offset [F] (nullable) receives the
+ *   locked offsets.  L < lock_samples is the reference's `unwrap()` panic: MODEM_ERR_INVALID. */
+int modem_gpu_demodulate_real(modem_ctx_t* ctx, const void* samples, uint32_t fmt, size_t F, size_t L,
+                              size_t lock_samples, const float* hilbert_taps, size_t n_hilbert, float* phase_offset,
+                              uint8_t* sym, uint8_t* bits, modem_c32_t* soft, modem_c32_t* filt);
 
 /* demodulate_count: the stream-ordered, device-resident form used inside a loopback: like
  * modem_gpu_demodulate (sym / bits nullable) but additionally compares every decided bit with

@@ -945,3 +945,112 @@ int orc_loopback(const orc_path_t* p, const uint8_t* bits, size_t F, size_t nbit
     free(tids);
     return rc;
 }
+
+/* ============================ src/bin sample paths ============================ */
+int orc_preamble(const orc_path_t* p, size_t F, size_t n, float amplitude, float* tx)
+{
+    for (size_t f = 0; f < F; ++f) {
+        orc_carrier_t carrier;
+        orc_carrier_new(&carrier, p->carrier_hz, p->sample_rate);
+        carrier.sample = p->sample0;
+        for (size_t j = 0; j < n; ++j) {
+            /* modulator.rs:54-61: phase = carrier.next(); Raw::next => (amplitude, 0.0) (phasor.rs:17-23) */
+            orc_iq_sample_t s = {orc_carrier_next(&carrier), amplitude, 0.0f};
+            orc_iq_modulate(&s, &tx[2 * (f * n + j)], &tx[2 * (f * n + j) + 1]);
+        }
+    }
+    return 0;
+}
+
+int orc_modulate_real(const orc_path_t* p, const uint8_t* bits, size_t F, size_t nbits, size_t preamble,
+                      float preamble_amplitude, float* out)
+{
+    orc_phasor_t ph0;
+    if (!path_phasor(p, &ph0)) return -1;
+    size_t sps = orc_samples_per_symbol(p->baud_rate, p->sample_rate);
+    size_t L = orc_frame_samples(p, nbits);
+    for (size_t f = 0; f < F; ++f) {
+        float* o = out + f * (preamble + L);
+        orc_carrier_t carrier; /* ONE carrier for tone and data (modulate.rs:71,120,128) */
+        orc_carrier_new(&carrier, p->carrier_hz, p->sample_rate);
+        carrier.sample = p->sample0;
+        float im;
+        for (size_t j = 0; j < preamble; ++j) { /* modulate.rs:120-125 */
+            orc_iq_sample_t s = {orc_carrier_next(&carrier), preamble_amplitude, 0.0f};
+            orc_iq_modulate(&s, &o[j], &im);
+        }
+        orc_phasor_t ph = ph0;
+        orc_source_t src;
+        if (path_evenodd(p)) orc_evenodd_new(&src, bits + f * nbits, nbits, sps, ph.bits_per_symbol);
+        else orc_bits_new(&src, bits + f * nbits, nbits, sps, ph.bits_per_symbol);
+        orc_iq_sample_t s;
+        size_t n = 0;
+        while (orc_digital_modulator_next(&carrier, &ph, &src, &s)) { /* modulate.rs:128-133 */
+            if (n >= L) return -4;
+            orc_iq_modulate(&s, &o[preamble + n], &im);
+            ++n;
+        }
+        if (n != L) return -4;
+    }
+    return 0;
+}
+
+int orc_demodulate_real(const orc_path_t* p, const float* x, const float* analytic_im, size_t F, size_t L, size_t lock,
+                        const float* hilbert, size_t n_hilbert, float* po_out, float* filt, uint8_t* sym, uint8_t* bits_out)
+{
+    if (L < lock) return -3;
+    float table[2 * 512];
+    size_t n_tables = orc_constellation(p, table, 512);
+    if (!n_tables) return -1;
+    size_t sps = orc_samples_per_symbol(p->baud_rate, p->sample_rate);
+    size_t bps = orc_bits_per_symbol(p), np = (size_t)1 << bps;
+    size_t q_off = path_q_offset(p);
+    size_t Lr = L - lock;
+    size_t K = orc_decided_symbols(p, Lr);
+    if (!hilbert) hilbert = orc_hilbert_taps(&n_hilbert);
+    float* rail_i = (float*)malloc((K ? K : 1) * sizeof(float));
+    for (size_t f = 0; f < F; ++f) {
+        const float* xf = x + f * L;
+        orc_fir_t hfir; /* demodulate.rs:31 */
+        if (!orc_fir_new(&hfir, hilbert, n_hilbert)) return -2;
+        orc_carrier_t carrier;
+        orc_carrier_new(&carrier, p->carrier_hz, p->sample_rate);
+        carrier.sample = p->sample0;
+        orc_demod_t d;
+        if (!orc_demod_new(&d, carrier, p->rx_taps, p->n_rx_taps)) return -2;
+        if (!lock) d.pll.phase_offset = p->phase_offset;
+        size_t t = 0;
+        for (; t < lock; ++t) { /* demodulator.rs:32-36 */
+            float im = analytic_im ? analytic_im[f * L + t] : orc_fir_add(&hfir, xf[t]); /* demodulate.rs:32-34 */
+            orc_demod_lock_step(&d, xf[t], im);
+        }
+        if (po_out) po_out[f] = d.pll.phase_offset;
+        for (size_t n = 0; n < Lr; ++n) { /* demodulate.rs:41-43 over demodulator.rs:44-55 */
+            float I, Q;
+            orc_demod_next(&d, xf[lock + n], &I, &Q);
+            if (filt) {
+                filt[2 * (f * Lr + n)] = I;
+                filt[2 * (f * Lr + n) + 1] = Q;
+            }
+            if ((sym || bits_out) && K) {
+                if (n >= p->decision_delay && (n - p->decision_delay) % sps == 0) {
+                    size_t k = (n - p->decision_delay) / sps;
+                    if (k < K) rail_i[k] = I;
+                }
+                if (n >= p->decision_delay + q_off && (n - p->decision_delay - q_off) % sps == 0) {
+                    size_t k = (n - p->decision_delay - q_off) / sps;
+                    if (k < K) {
+                        uint8_t s = slice_point(table + 2 * np * (k % n_tables), np, p->slicer_gain, rail_i[k], Q);
+                        if (sym) sym[f * K + k] = s;
+                        if (bits_out)
+                            for (size_t j = 0; j < bps; ++j) bits_out[(f * K + k) * bps + j] = (uint8_t)((s >> (bps - 1 - j)) & 1);
+                    }
+                }
+            }
+        }
+        orc_demod_free(&d);
+        orc_fir_free(&hfir);
+    }
+    free(rail_i);
+    return 0;
+}

@@ -240,6 +240,26 @@ int orc_loopback(const orc_path_t* p, const uint8_t* bits, size_t F, size_t nbit
                  uint8_t* sym /*nullable [F][K]*/, uint8_t* bits_out /*nullable*/,
                  uint64_t counters[2]);
 
+
+/* ---- src/bin drivers: the two binaries' sample paths, composed from the objects above ---- */
+/* src/bin/modulate.rs:118-133 without --iq: `preamble` samples of Modulator + phasor::Raw(amplitude)
+ * (modulator.rs:51-62, phasor.rs:5-24) mapped through `x.modulate().re`, then the DigitalModulator's
+ * samples `.re`, all on ONE Carrier (the counter carries over, modulate.rs:120,128).
+ * out [F][preamble + L] f32. */
+int orc_modulate_real(const orc_path_t* p, const uint8_t* bits, size_t F, size_t nbits, size_t preamble,
+                      float preamble_amplitude, float* out);
+/* Complex samples of the same tone: tx [F][n][2]. */
+int orc_preamble(const orc_path_t* p, size_t F, size_t n, float amplitude, float* tx);
+/* src/bin/demodulate.rs:29-43 per frame: x = sample as f32 (real input x[F][L]); analytic = (x, hilbert.add(x));
+ * Demodulator::new(carrier, analytic, lowpass); lock_phase() over the first `lock` samples
+ * (demodulator.rs:32-36); then Demodulator::next for the remaining L - lock samples.
+ * analytic_im (nullable) [F][L]: caller-supplied imaginary parts instead of the Hilbert FIR.
+ * po_out [F] (nullable) = PLL.phase_offset after the lock; filt [F][L-lock][2] (nullable) the (I,Q) stream the
+ * binary prints; sym/bits_out (nullable) the decimator/slicer extension over that stream.
+ * lock == 0: no lock, phase offset = p->phase_offset.  Returns -3 if L < lock (the reference's unwrap panic). */
+int orc_demodulate_real(const orc_path_t* p, const float* x, const float* analytic_im, size_t F, size_t L, size_t lock,
+                        const float* hilbert, size_t n_hilbert, float* po_out, float* filt, uint8_t* sym, uint8_t* bits_out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -137,6 +137,10 @@ def lib():
         L.orc_constellation.restype = sz; L.orc_constellation.argtypes = [PA, f32p, sz]
         L.orc_modulate.restype = C.c_int; L.orc_modulate.argtypes = [PA, u8p, sz, sz, f32p, f32p]
         L.orc_demodulate.restype = C.c_int; L.orc_demodulate.argtypes = [PA, f32p, sz, sz, f32p, u8p, u8p]
+        L.orc_preamble.restype = C.c_int; L.orc_preamble.argtypes = [PA, sz, sz, f32, f32p]
+        L.orc_modulate_real.restype = C.c_int; L.orc_modulate_real.argtypes = [PA, u8p, sz, sz, sz, f32, f32p]
+        L.orc_demodulate_real.restype = C.c_int
+        L.orc_demodulate_real.argtypes = [PA, f32p, f32p, sz, sz, sz, f32p, sz, f32p, f32p, u8p, u8p]
         L.orc_loopback.restype = C.c_int
         L.orc_loopback.argtypes = [PA, u8p, sz, sz, f32, C.c_uint64, C.c_uint64, C.c_int, u8p, u8p,
                                    C.POINTER(C.c_uint64)]
@@ -250,3 +254,38 @@ class OraclePath:
                                 _u8p(sym), _u8p(bo), cnt)
         assert rc == 0, rc
         return sym, bo, (cnt[0], cnt[1])
+
+    # ---- src/bin sample paths -------------------------------------------------------------
+    def preamble(self, F, n, amplitude=1.0):
+        tx = np.zeros((F, n, 2), np.float32)
+        assert lib().orc_preamble(C.byref(self.p), F, n, amplitude, _f32p(tx)) == 0
+        return tx
+
+    def modulate_real(self, bits, preamble=0, preamble_amplitude=1.0):
+        """What src/bin/modulate.rs writes without --iq: [F][preamble + L] f32."""
+        bits = np.ascontiguousarray(bits, np.uint8)
+        F, nbits = bits.shape
+        out = np.zeros((F, preamble + self.frame_samples(nbits)), np.float32)
+        rc = lib().orc_modulate_real(C.byref(self.p), _u8p(bits), F, nbits, preamble, preamble_amplitude, _f32p(out))
+        assert rc == 0, rc
+        return out
+
+    def demodulate_real(self, x, lock=64, analytic_im=None, hilbert=None, want_filt=True):
+        """src/bin/demodulate.rs per frame: x [F][L] real (any numeric dtype, `x as f32`).  Returns
+        (phase_offset [F], filt [F][L-lock][2], sym, bits)."""
+        x = np.ascontiguousarray(x, np.float32)
+        F, L = x.shape
+        Lr = L - lock
+        K = self.decided_symbols(Lr)
+        po = np.zeros(F, np.float32)
+        filt = np.zeros((F, Lr, 2), np.float32) if want_filt else None
+        sym = np.zeros((F, K), np.uint8)
+        bits = np.zeros((F, K * self.bps), np.uint8)
+        im = None if analytic_im is None else np.ascontiguousarray(analytic_im, np.float32)
+        h = None if hilbert is None else np.ascontiguousarray(hilbert, np.float32)
+        rc = lib().orc_demodulate_real(C.byref(self.p), _f32p(x), _f32p(im), F, L, lock, _f32p(h), 0 if h is None else len(h),
+                                       _f32p(po), _f32p(filt), _u8p(sym), _u8p(bits))
+        if rc == -3:
+            raise ValueError("called `Option::unwrap()` on a `None` value")  # demodulator.rs:34
+        assert rc == 0, rc
+        return po, filt, sym, bits

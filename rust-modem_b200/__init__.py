@@ -8,9 +8,10 @@ is loaded with `__graft_entry__.load_package()` (importlib) under the module nam
 sm_100 GPU every compute call raises.
 """
 from .capi import (ModemError, Modem, ModemCfg, lib, build_library, library_path, host_constellation,
-                   lowpass_taps, rrc_taps, sample_freq, samples_per_symbol, FLAG_FUSED_MAC)
+                   lowpass_taps, rrc_taps, hilbert_taps, host_phasor, Phasor, sample_freq, samples_per_symbol, FLAG_FUSED_MAC,
+                   STATEFUL_NAMES)
 
 from .sharding import shard_range, shard_channels
 
 __all__ = ["shard_range", "shard_channels", "ModemError", "Modem", "ModemCfg", "lib", "build_library", "library_path", "host_constellation",
-           "lowpass_taps", "rrc_taps", "sample_freq", "samples_per_symbol", "FLAG_FUSED_MAC"]
+           "lowpass_taps", "rrc_taps", "hilbert_taps", "host_phasor", "Phasor", "STATEFUL_NAMES", "sample_freq", "samples_per_symbol", "FLAG_FUSED_MAC"]

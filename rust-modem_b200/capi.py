@@ -30,6 +30,18 @@ class ModemCfg(C.Structure):
     ]
 
 
+class Phasor(C.Structure):
+    """modem_phasor_t (include/modem_gpu.h): the stateful / time-varying mappers."""
+    _fields_ = [("struct_size", C.c_uint32), ("kind", C.c_uint32), ("bits_per_symbol", C.c_uint32),
+                ("amplitude", C.c_float), ("deviation", C.c_float), ("phase", C.c_float), ("shift", C.c_float),
+                ("mfsk_increase_map", C.c_uint32)]
+
+
+PHASOR_TABLE, PHASOR_BFSK, PHASOR_MFSK, PHASOR_CPFSK, PHASOR_MSK, PHASOR_DMPSK = range(6)
+SAMPLES_C32, SAMPLES_F32, SAMPLES_I16 = 0, 1, 2
+STATEFUL_NAMES = ("bfsk", "mfsk", "16cpfsk", "msk", "dqpsk", "dbpsk")
+
+
 class Ring(C.Structure):
     _fields_ = [("start", C.c_uint8), ("end", C.c_uint8), ("radius", C.c_float), ("phase", C.c_float)]
 
@@ -75,6 +87,13 @@ def lib():
     L.modem_const_by_name.argtypes = [C.c_char_p, f32p, u32p, u32p]
     L.modem_lowpass_taps.restype = f32p; L.modem_lowpass_taps.argtypes = [C.POINTER(sz)]
     L.modem_rrc_taps.argtypes = [f32p, sz, sz, C.c_double]
+    L.modem_hilbert_taps.restype = f32p; L.modem_hilbert_taps.argtypes = [C.POINTER(sz)]
+    L.modem_phasor_by_name.argtypes = [C.c_char_p, sz, sz, C.POINTER(Phasor), u32p]
+    L.modem_gpu_set_phasor.argtypes = [vp, C.POINTER(Phasor)]
+    L.modem_gpu_preamble.argtypes = [vp, sz, sz, f32, vp]
+    L.modem_gpu_modulate_real.argtypes = [vp, u8p, sz, sz, sz, f32, vp]
+    L.modem_gpu_lock_phase.argtypes = [vp, vp, C.c_uint32, sz, sz, f32p, sz, sz, vp]
+    L.modem_gpu_demodulate_real.argtypes = [vp, vp, C.c_uint32, sz, sz, sz, f32p, sz, vp, vp, vp, vp, vp]
     L.modem_sigma_for_ebn0.restype = f32; L.modem_sigma_for_ebn0.argtypes = [C.POINTER(ModemCfg), C.c_double]
     L.modem_gpu_device_count.argtypes = [C.POINTER(C.c_int)]
     L.modem_gpu_create.argtypes = [C.POINTER(vp), C.c_int, C.POINTER(ModemCfg)]
@@ -127,6 +146,21 @@ def lowpass_taps():
     return np.ctypeslib.as_array(p, shape=(n.value,)).copy()
 
 
+def hilbert_taps():
+    n = C.c_size_t()
+    p = lib().modem_hilbert_taps(C.byref(n))
+    return np.ctypeslib.as_array(p, shape=(n.value,)).copy()
+
+
+def host_phasor(name, baud_rate, sample_rate):
+    """(Phasor, bps, evenodd) for a stateful src/bin/modulate.rs -m name (bfsk, mfsk, 16cpfsk, msk, dqpsk, dbpsk)."""
+    ph, eo = Phasor(), C.c_uint32()
+    bps = lib().modem_phasor_by_name(name.encode(), baud_rate, sample_rate, C.byref(ph), C.byref(eo))
+    if bps < 0:
+        raise ModemError(bps, f"invalid digital modulation {name!r}")
+    return ph, bps, bool(eo.value)
+
+
 def rrc_taps(span, sps, beta):
     out = np.empty(span * sps + 1, np.float32)
     rc = lib().modem_rrc_taps(_f32p(out), span, sps, beta)
@@ -173,7 +207,12 @@ class Modem:
                  tx_taps=None, rx_taps=None, phase_offset=0.0, decision_delay=0, slicer_gain=1.0, rx_gain=2.0,
                  flags=0, device=0, const_iq=None, bps=None, q_offset=None):
         L = lib()
-        if const_iq is None:
+        phasor = None
+        if const_iq is None and scheme in STATEFUL_NAMES:
+            # TX-only schemes: the context still needs a (dummy) table of the right size for its slicer
+            phasor, bps, evenodd = host_phasor(scheme, baud_rate, sample_rate)
+            const_iq = np.zeros((1, 1 << bps, 2), np.float32)
+        elif const_iq is None:
             const_iq, bps, evenodd = host_constellation(scheme)
         else:
             const_iq = np.ascontiguousarray(const_iq, np.float32)
@@ -206,6 +245,9 @@ class Modem:
         rc = L.modem_gpu_create(C.byref(self._ctx), device, C.byref(cfg))
         if rc:
             raise ModemError(rc, (L.modem_gpu_last_error(None) or b"").decode() or L.modem_gpu_strerror(rc).decode())
+        self.phasor = phasor
+        if phasor is not None:
+            self._ck(L.modem_gpu_set_phasor(self._ctx, C.byref(phasor)))
 
     # -- plumbing
     def _ck(self, rc):
@@ -308,6 +350,56 @@ class Modem:
         F, L, _ = buf.shape
         self.awgn_inplace(buf, F, L, sigma, seed, frame0)
         return buf
+
+    # -- src/bin sample paths
+    def preamble(self, F, n, amplitude=1.0):
+        tx = np.zeros((F, n, 2), np.float32)
+        self._ck(lib().modem_gpu_preamble(self._ctx, F, n, amplitude, _ptr(tx)))
+        return tx
+
+    def modulate_real(self, bits, preamble=0, preamble_amplitude=1.0):
+        """The f32 stream src/bin/modulate.rs writes without --iq: [F][preamble + L]."""
+        bits = np.ascontiguousarray(bits, np.uint8)
+        F, nbits = bits.shape
+        out = np.zeros((F, preamble + self.frame_samples(nbits)), np.float32)
+        self._ck(lib().modem_gpu_modulate_real(self._ctx, _ptr(bits), F, nbits, preamble, preamble_amplitude, _ptr(out)))
+        return out
+
+    @staticmethod
+    def _fmt(x):
+        if x.dtype == np.int16:
+            return SAMPLES_I16
+        if x.dtype == np.float32 and x.ndim == 3:
+            return SAMPLES_C32
+        if x.dtype == np.float32:
+            return SAMPLES_F32
+        raise TypeError(x.dtype)
+
+    def lock_phase(self, x, lock=64, hilbert=None):
+        x = np.ascontiguousarray(x)
+        F, L = x.shape[:2]
+        po = np.zeros(F, np.float32)
+        h = None if hilbert is None else np.ascontiguousarray(hilbert, np.float32)
+        self._ck(lib().modem_gpu_lock_phase(self._ctx, _ptr(x), self._fmt(x), F, L, _f32p(h), 0 if h is None else len(h),
+                                            lock, _ptr(po)))
+        return po
+
+    def demodulate_real(self, x, lock=64, hilbert=None, want_filt=True, want_soft=False):
+        """src/bin/demodulate.rs per frame: x [F][L] int16 / float32 real samples (or [F][L][2] analytic)."""
+        x = np.ascontiguousarray(x)
+        F, L = x.shape[:2]
+        Lr = L - lock
+        K = self.decided_symbols(Lr) if Lr > 0 else 0
+        po = np.zeros(F, np.float32)
+        sym = np.zeros((F, K), np.uint8)
+        bits = np.zeros((F, K * self.bps), np.uint8)
+        soft = np.zeros((F, K, 2), np.float32) if want_soft else None
+        filt = np.zeros((F, max(Lr, 0), 2), np.float32) if want_filt else None
+        h = None if hilbert is None else np.ascontiguousarray(hilbert, np.float32)
+        self._ck(lib().modem_gpu_demodulate_real(self._ctx, _ptr(x), self._fmt(x), F, L, lock, _f32p(h),
+                                                 0 if h is None else len(h), _ptr(po), _ptr(sym), _ptr(bits),
+                                                 _ptr(soft), _ptr(filt)))
+        return {"phase_offset": po, "sym": sym, "bits": bits, "soft": soft, "filt": filt}
 
     def loopback(self, bits, sigma=0.0, seed=0, frame0=0, want_tx=False):
         bits = np.ascontiguousarray(bits, np.uint8)

@@ -194,6 +194,61 @@ const float* modem_lowpass_taps(size_t* n)
     return full;
 }
 
+const float* modem_hilbert_taps(size_t* n)
+{
+    /* src/bin/demodulate.rs:48-72 (Hilbert transformer "generated with matlab") */
+    static const float h[23] = {-0.007576f, -2.803e-16f, -0.019824f, 3.7096e-16f, -0.044089f, 1.3201e-16f,
+                                -0.089244f, -3.2694e-16f, -0.18728f, -1.6739e-16f, -0.62794f, 0.0f,
+                                0.62794f, 1.6739e-16f, 0.18728f, 3.2694e-16f, 0.089244f, -1.3201e-16f,
+                                0.044089f, -3.7096e-16f, 0.019824f, 2.803e-16f, 0.007576f};
+    if (n) *n = 23;
+    return h;
+}
+
+int modem_phasor_by_name(const char* name, size_t br, size_t sr, modem_phasor_t* out, uint32_t* evenodd)
+{
+    /* the stateful rows of src/bin/modulate.rs:74-95, AMPLITUDE = 1.0 (modulate.rs:14) */
+    if (!name || !out || br == 0 || sr == 0) return MODEM_ERR_INVALID;
+    modem_phasor_t p;
+    memset(&p, 0, sizeof p);
+    p.struct_size = sizeof p;
+    p.amplitude = 1.0f;
+    if (evenodd) *evenodd = 0;
+    if (!strcmp(name, "bfsk")) { /* BFSK::new(Freq::new(200, sr), A) */
+        p.kind = MODEM_PHASOR_BFSK;
+        p.bits_per_symbol = 1;
+        p.deviation = modem_sample_freq(200, sr);
+    } else if (!strcmp(name, "mfsk")) { /* MFSK::new(4, Freq::new(50, sr), A, IncreaseMap) */
+        p.kind = MODEM_PHASOR_MFSK;
+        p.bits_per_symbol = 4;
+        p.deviation = modem_sample_freq(50, sr);
+        p.mfsk_increase_map = 1;
+    } else if (!strcmp(name, "16cpfsk")) { /* CPFSK::new(4, rates, A, 1): Freq::new(deviation * baud / 2, sr) (cpfsk.rs:19-20) */
+        p.kind = MODEM_PHASOR_CPFSK;
+        p.bits_per_symbol = 4;
+        p.deviation = modem_sample_freq(1 * br / 2, sr);
+    } else if (!strcmp(name, "msk")) { /* MSK::new(A, sps), fed by EvenOddOffset (modulate.rs:101-105) */
+        if (modem_samples_per_symbol(br, sr) % 2) return MODEM_ERR_INVALID; /* msk.rs:13 assert */
+        p.kind = MODEM_PHASOR_MSK;
+        p.bits_per_symbol = 2;
+        if (evenodd) *evenodd = 1;
+    } else if (!strcmp(name, "dqpsk")) { /* DMPSK::new(2, A, PI/4, PI/2) */
+        p.kind = MODEM_PHASOR_DMPSK;
+        p.bits_per_symbol = 2;
+        p.phase = PI32 / 4.0f;
+        p.shift = PI32 / 2.0f;
+    } else if (!strcmp(name, "dbpsk")) { /* DMPSK::new(1, A, PI/4, PI) */
+        p.kind = MODEM_PHASOR_DMPSK;
+        p.bits_per_symbol = 1;
+        p.phase = PI32 / 4.0f;
+        p.shift = PI32;
+    } else {
+        return MODEM_ERR_UNSUPPORTED;
+    }
+    *out = p;
+    return (int)p.bits_per_symbol;
+}
+
 int modem_rrc_taps(float* out, size_t span, size_t sps, double beta)
 {
     if (!out || span == 0 || sps == 0 || beta < 0.0 || beta > 1.0) return MODEM_ERR_INVALID;

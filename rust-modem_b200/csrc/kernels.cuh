@@ -62,6 +62,12 @@ __global__ void __launch_bounds__(kThreads) tx_rect_kernel(const __grid_constant
                 out[v] = mix_iq(bb[v].x, bb[v].y, cs[u][v], sn[u][v]);
             }
             const u64 o = f * a.L + n0[u];
+            if (a.re) {
+                float* r = a.re + f * a.re_stride + a.re_offset + n0[u];
+#pragma unroll
+                for (int v = 0; v < VEC; ++v)
+                    if (n0[u] + v < a.L) __stcs(r + v, out[v].x);
+            }
             if (VEC == 2) {
                 if (a.tx) __stcs(reinterpret_cast<float4*>(a.tx + o), make_float4(out[0].x, out[0].y, out[VEC - 1].x, out[VEC - 1].y));
                 if (a.iq) __stcs(reinterpret_cast<float4*>(a.iq + o), make_float4(bb[0].x, bb[0].y, bb[VEC - 1].x, bb[VEC - 1].y));
@@ -147,7 +153,11 @@ __global__ void __launch_bounds__(kThreads) tx_shaped_generic_kernel(const __gri
             float2 cs = s_cs[n - nb];
             const u64 o = f * a.L + n;
             if (a.iq) __stcs(a.iq + o, make_float2(ai, aq));
-            if (a.tx) __stcs(a.tx + o, mix_iq(ai, aq, cs.x, cs.y));
+            if (a.tx || a.re) {
+                const float2 m = mix_iq(ai, aq, cs.x, cs.y);
+                if (a.tx) __stcs(a.tx + o, m);
+                if (a.re) __stcs(a.re + f * a.re_stride + a.re_offset + n, m.x);
+            }
         }
     }
 }
@@ -236,14 +246,13 @@ __global__ void __launch_bounds__(kThreads) rx_generic_kernel(const __grid_const
 
     uint32_t err = 0, cmp = 0;
     for (u64 f = f0; f < f1; ++f) {
-        const float2* frame = a.rx + f * a.L;
         __syncthreads();
         for (uint32_t j = threadIdx.x; j < R; j += kThreads) {
             long long n = nb + j;
             float2 v = make_float2(0.0f, 0.0f);
             if (n >= 0 && (u64)n < a.L) {
                 float2 cs = s_cs[j];
-                v = rx_mix(a, frame, a.nz.frame0 + f, (u64)n, cs.x, cs.y);
+                v = rx_mix(a, f, a.nz.frame0 + f, (u64)n, cs.x, cs.y);
             }
             s_vi[j] = v.x;
             s_vq[j] = v.y;
@@ -288,7 +297,6 @@ __global__ void __launch_bounds__(kThreads) rx_fullrate_kernel(const __grid_cons
 
     const u64 f = blockIdx.y;
     const float w = chan_w(a.ch, f), po = chan_po(a.ch, f);
-    const float2* frame = a.rx + f * a.L;
     const u64 t0 = (u64)blockIdx.x * TILE;
     const long long nb = (long long)t0 - (long long)(N - 1);
     for (uint32_t j = threadIdx.x; j < R; j += kThreads) {
@@ -297,7 +305,7 @@ __global__ void __launch_bounds__(kThreads) rx_fullrate_kernel(const __grid_cons
         if (n >= 0 && (u64)n < a.L) {
             float s, c;
             mg_sincosf(__fadd_rn(nco_phase(w, a.sample0 + (u64)n), po), &s, &c);
-            v = rx_mix(a, frame, a.nz.frame0 + f, (u64)n, c, s);
+            v = rx_mix(a, f, a.nz.frame0 + f, (u64)n, c, s);
         }
         s_vi[j] = v.x;
         s_vq[j] = v.y;

@@ -15,6 +15,7 @@
 
 #include "../../include/modem_gpu.h"
 #include "kernels.cuh"
+#include "frontend.cuh"
 #include "launch.h"
 
 using mg::u64;
@@ -44,6 +45,10 @@ struct modem_ctx {
     size_t n_channels = 0, frames_per_channel = 1;
     u64* d_counters = nullptr;
     Scratch s_bits, s_tx, s_iq, s_rx, s_sym, s_bits_out, s_soft, s_filt;
+    /* stateful phasor (modem_gpu_set_phasor) and the carrier-recovery front end */
+    modem_phasor_t phasor{};
+    bool phasor_on = false;
+    Scratch s_state, s_re, s_raw, s_po, s_hilbert;
     /* host-buffer loopback pipeline: three lanes, each with its own stream and chunk buffers */
     struct Lane {
         cudaStream_t s = nullptr;
@@ -188,6 +193,7 @@ mg::ChannelView channel_view(const modem_ctx* ctx)
     v.cs_tab = nullptr;
     v.cs_len = 0;
     v.cs_ch0 = 0;
+    v.po_frame = nullptr;
     return v;
 }
 
@@ -255,10 +261,24 @@ int attach_carrier_table(modem_ctx* ctx, mg::ChannelView& view, u64 F, u64 len, 
 }
 
 /* ------------------------------------------------------------------ TX launch */
-int launch_tx(modem_ctx* ctx, const uint8_t* d_bits, u64 F, u64 nbits, float2* d_tx, float2* d_iq)
+/* the real-part wire output of src/bin/modulate.rs (generic kernels only) */
+struct RealOut {
+    float* re = nullptr;
+    u64 stride = 0, offset = 0;
+    u64 sample_skip = 0; /* samples the shared Carrier already produced (the preamble, modulate.rs:120,128) */
+};
+
+int launch_tx_phasor(modem_ctx* ctx, mg::TxArgs& a);
+
+int launch_tx(modem_ctx* ctx, const uint8_t* d_bits, u64 F, u64 nbits, float2* d_tx, float2* d_iq, const RealOut* ro = nullptr)
 {
     const modem_cfg_t& c = ctx->cfg;
     mg::TxArgs a{};
+    if (ro) {
+        a.re = ro->re;
+        a.re_stride = ro->stride;
+        a.re_offset = ro->offset;
+    }
     a.bits = d_bits;
     a.nbits = nbits;
     a.tx = d_tx;
@@ -273,19 +293,21 @@ int launch_tx(modem_ctx* ctx, const uint8_t* d_bits, u64 F, u64 nbits, float2* d
     a.n_const = 1u << c.bits_per_symbol;
     a.q_offset = c.q_offset;
     a.ch = channel_view(ctx);
-    a.sample0 = c.sample0;
+    a.sample0 = c.sample0 + (ro ? ro->sample_skip : 0);
     a.taps = ctx->d_tx_taps;
     a.n_taps = c.n_tx_taps;
     if (F == 0 || a.L == 0) return MODEM_OK;
     if (a.nsym >= (1ull << 32)) return fail(ctx, MODEM_ERR_UNSUPPORTED, "more than 2^32 symbols per frame");
+    if (ctx->phasor_on) return launch_tx_phasor(ctx, a);
     const bool fma = (c.flags & MODEM_FLAG_FUSED_MAC) != 0;
     const bool vec_ok = (a.L % 2 == 0) && aligned16(d_tx) && aligned16(d_iq);
+    const bool plain = ro == nullptr; /* the tuned kernels write complex samples and take the carrier from the NCO table */
 
     if (c.n_tx_taps == 0) {
         const uint32_t bps = c.bits_per_symbol;
         const bool word_ok = mg::tx_rect_fast_supported(bps) && (nbits % bps == 0) &&
                              ((reinterpret_cast<uintptr_t>(d_bits) % bps) == 0);
-        const bool fast = !ctx->force_generic && vec_ok && d_tx && !d_iq && c.q_offset == 0 && c.n_tables == 1 &&
+        const bool fast = plain && !ctx->force_generic && vec_ok && d_tx && !d_iq && c.q_offset == 0 && c.n_tables == 1 &&
                           (c.samples_per_symbol % 2 == 0) && word_ok && a.L < (1ull << 32);
         if (fast) {
             a.frames_per_block = frames_per_block(ctx, F, mg::tx_rect_fast_tiles(a.L));
@@ -301,7 +323,7 @@ int launch_tx(modem_ctx* ctx, const uint8_t* d_bits, u64 F, u64 nbits, float2* d
             if (vec == 2) mg::tx_rect_kernel<2><<<grid, mg::kThreads, 0, ctx->stream>>>(a);
             else mg::tx_rect_kernel<1><<<grid, mg::kThreads, 0, ctx->stream>>>(a);
         }
-    } else if (!ctx->force_generic && mg::tx_shaped_fast_supported(c.samples_per_symbol, c.n_tx_taps) && c.q_offset == 0 &&
+    } else if (plain && !ctx->force_generic && mg::tx_shaped_fast_supported(c.samples_per_symbol, c.n_tx_taps) && c.q_offset == 0 &&
                d_tx && !d_iq && vec_ok) {
         a.frames_per_block = frames_per_block(ctx, F, mg::tx_shaped_fast_tiles(a.nsym));
         int rc = attach_carrier_table(ctx, a.ch, F, a.L, false);
@@ -331,9 +353,17 @@ int launch_tx(modem_ctx* ctx, const uint8_t* d_bits, u64 F, u64 nbits, float2* d
 }
 
 /* ------------------------------------------------------------------ RX launch */
+/* real-valued input of the demodulate binary (generic kernels only): see RxArgs::raw */
+struct RawSrc {
+    const void* raw = nullptr;
+    uint32_t fmt = 0;
+    u64 stride = 0, skip = 0;
+    const float* d_po = nullptr; /* per-frame PLL.phase_offset (nullable) */
+};
+
 int launch_rx(modem_ctx* ctx, const float2* d_rx, u64 F, u64 L, uint8_t* d_sym, uint8_t* d_bits, float2* d_soft,
               float2* d_filt, const uint8_t* d_ref, u64 ref_stride, u64* d_counters, float sigma, uint64_t seed,
-              uint64_t frame0)
+              uint64_t frame0, const RawSrc* src = nullptr)
 {
     const modem_cfg_t& c = ctx->cfg;
     mg::RxArgs a{};
@@ -363,6 +393,14 @@ int launch_rx(modem_ctx* ctx, const float2* d_rx, u64 F, u64 L, uint8_t* d_sym, 
     a.nz.sigma = sigma;
     a.nz.seed = seed;
     a.nz.frame0 = frame0;
+    if (src) {
+        a.raw = src->raw;
+        a.rx_fmt = src->fmt;
+        a.raw_stride = src->stride;
+        a.raw_skip = src->skip;
+        a.sample0 = c.sample0 + src->skip; /* the demodulator's Carrier ran through the lock (demodulator.rs:34) */
+        a.ch.po_frame = src->d_po;
+    }
     if (F == 0 || L == 0) return MODEM_OK;
     const bool fma = (c.flags & MODEM_FLAG_FUSED_MAC) != 0;
     const uint32_t N = c.n_rx_taps, sps = c.samples_per_symbol;
@@ -385,7 +423,7 @@ int launch_rx(modem_ctx* ctx, const float2* d_rx, u64 F, u64 L, uint8_t* d_sym, 
     }
     if (a.K == 0 || !(d_sym || d_bits || d_soft || d_ref)) return MODEM_OK;
 
-    const bool fast_ok = !ctx->force_generic && sps == 8 && c.q_offset == 0 && (L % 2 == 0) && aligned16(d_rx) &&
+    const bool fast_ok = !src && !ctx->force_generic && sps == 8 && c.q_offset == 0 && (L % 2 == 0) && aligned16(d_rx) &&
                          mg::rx_fast_supported(N);
     if (fast_ok) {
         a.frames_per_block = frames_per_block(ctx, F, mg::rx_fast_tiles(N, a.K, ctx->rx_variant));
@@ -409,6 +447,10 @@ int launch_rx(modem_ctx* ctx, const float2* d_rx, u64 F, u64 L, uint8_t* d_sym, 
         const size_t smem = R * 16 + (size_t)N * 4;
         const u64 tiles = (a.K + TS - 1) / TS;
         a.frames_per_block = frames_per_block(ctx, F, tiles);
+        if (src && src->d_po) { /* every frame has its own phase offset: the CTA's NCO values serve one frame */
+            if (F > 65535) return fail(ctx, MODEM_ERR_UNSUPPORTED, "per-frame phase offsets limited to 65535 frames per call");
+            a.frames_per_block = 1;
+        }
         dim3 grid((unsigned)tiles, (unsigned)((F + a.frames_per_block - 1) / a.frames_per_block));
         if (fma) {
             CK(ctx, cudaFuncSetAttribute(mg::rx_generic_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -418,6 +460,82 @@ int launch_rx(modem_ctx* ctx, const float2* d_rx, u64 F, u64 L, uint8_t* d_sym, 
             mg::rx_generic_kernel<false><<<grid, mg::kThreads, smem, ctx->stream>>>(a);
         }
     }
+    ctx->launches++;
+    CK(ctx, cudaGetLastError());
+    return MODEM_OK;
+}
+
+
+/* ------------------------------------------------------------------ stateful phasors (TX) */
+int launch_tx_phasor(modem_ctx* ctx, mg::TxArgs& a)
+{
+    const modem_phasor_t& ph = ctx->phasor;
+    mg::PhasorArgs p{};
+    p.kind = ph.kind;
+    p.bps = ph.bits_per_symbol;
+    p.increase_map = ph.mfsk_increase_map;
+    p.max_symbol = (int)((1u << ph.bits_per_symbol) - 1u);
+    p.amplitude = ph.amplitude;
+    p.deviation = ph.deviation;
+    p.phase = ph.phase;
+    p.shift = ph.shift;
+    p.samples_per_bit = (float)(a.sps / 2); /* msk.rs:17 */
+    if (a.n_taps) return fail(ctx, MODEM_ERR_UNSUPPORTED, "tx_taps are not combined with a stateful phasor");
+    const bool scan = ph.kind == MODEM_PHASOR_BFSK || ph.kind == MODEM_PHASOR_MFSK || ph.kind == MODEM_PHASOR_DMPSK;
+    if (scan) {
+        int rc = ensure(ctx, ctx->s_state, a.F * a.nsym * sizeof(float));
+        if (rc) return rc;
+        p.state = (const float*)ctx->s_state.p;
+        const unsigned blocks = (unsigned)((a.F + 127) / 128);
+        mg::phasor_scan_kernel<<<blocks, 128, 0, ctx->stream>>>(a.bits, a.nbits, a.F, a.nsym, a.sps, a.sample0, p, (float*)ctx->s_state.p);
+        ctx->launches++;
+        CK(ctx, cudaGetLastError());
+    }
+    const u64 tile = (u64)mg::kThreads * 4;
+    const u64 tiles = (a.L + tile - 1) / tile;
+    a.frames_per_block = frames_per_block(ctx, a.F, tiles);
+    dim3 grid((unsigned)tiles, (unsigned)((a.F + a.frames_per_block - 1) / a.frames_per_block));
+    switch (ph.kind) {
+    case MODEM_PHASOR_BFSK: mg::tx_phasor_kernel<mg::kPhBfsk><<<grid, mg::kThreads, 0, ctx->stream>>>(a, p); break;
+    case MODEM_PHASOR_MFSK: mg::tx_phasor_kernel<mg::kPhMfsk><<<grid, mg::kThreads, 0, ctx->stream>>>(a, p); break;
+    case MODEM_PHASOR_CPFSK: mg::tx_phasor_kernel<mg::kPhCpfsk><<<grid, mg::kThreads, 0, ctx->stream>>>(a, p); break;
+    case MODEM_PHASOR_MSK: mg::tx_phasor_kernel<mg::kPhMsk><<<grid, mg::kThreads, 0, ctx->stream>>>(a, p); break;
+    case MODEM_PHASOR_DMPSK: mg::tx_phasor_kernel<mg::kPhDmpsk><<<grid, mg::kThreads, 0, ctx->stream>>>(a, p); break;
+    default: return fail(ctx, MODEM_ERR_INVALID, "unknown phasor kind");
+    }
+    ctx->launches++;
+    CK(ctx, cudaGetLastError());
+    return MODEM_OK;
+}
+
+/* ------------------------------------------------------------------ PLL lock launch */
+size_t sample_bytes(uint32_t fmt) { return fmt == MODEM_SAMPLES_C32 ? 8 : fmt == MODEM_SAMPLES_F32 ? 4 : 2; }
+
+int launch_lock(modem_ctx* ctx, const void* d_samples, uint32_t fmt, u64 F, u64 stride, const float* hilbert, size_t n_h,
+                size_t lock, float* d_po)
+{
+    mg::LockArgs a{};
+    a.samples = d_samples;
+    a.fmt = fmt;
+    a.F = F;
+    a.stride = stride;
+    a.lock = (uint32_t)lock;
+    a.ch = channel_view(ctx);
+    a.sample0 = ctx->cfg.sample0;
+    a.po = d_po;
+    if (fmt != MODEM_SAMPLES_C32) {
+        size_t n = n_h;
+        const float* h = hilbert;
+        if (!h) h = modem_hilbert_taps(&n);
+        if (n == 0 || n > 4096) return fail(ctx, MODEM_ERR_INVALID, "lock_phase: bad Hilbert tap count");
+        int rc = ensure(ctx, ctx->s_hilbert, n * sizeof(float));
+        if (rc) return rc;
+        CK(ctx, cudaMemcpyAsync(ctx->s_hilbert.p, h, n * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+        a.htaps = (const float*)ctx->s_hilbert.p;
+        a.n_h = (uint32_t)n;
+    }
+    if (F == 0) return MODEM_OK;
+    mg::lock_phase_kernel<<<(unsigned)((F + 63) / 64), 64, 0, ctx->stream>>>(a);
     ctx->launches++;
     CK(ctx, cudaGetLastError());
     return MODEM_OK;
@@ -562,7 +680,8 @@ void modem_gpu_destroy(modem_ctx_t* ctx)
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     void* ptrs[] = {ctx->d_lut, ctx->d_slut, ctx->d_tx_taps, ctx->d_rx_taps, ctx->d_chan_w, ctx->d_chan_po, ctx->d_counters,
-                    ctx->s_bits.p, ctx->s_tx.p, ctx->s_iq.p, ctx->s_rx.p, ctx->s_sym.p, ctx->s_bits_out.p, ctx->s_soft.p, ctx->s_filt.p};
+                    ctx->s_bits.p, ctx->s_tx.p, ctx->s_iq.p, ctx->s_rx.p, ctx->s_sym.p, ctx->s_bits_out.p, ctx->s_soft.p, ctx->s_filt.p,
+                    ctx->s_state.p, ctx->s_re.p, ctx->s_raw.p, ctx->s_po.p, ctx->s_hilbert.p};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     for (auto& ln : ctx->lanes) {
@@ -660,6 +779,147 @@ int modem_gpu_modulate(modem_ctx_t* ctx, const uint8_t* bits, size_t F, size_t n
     if (!rc) rc = finish_out(ctx, st);
     if (!rc) rc = finish_out(ctx, si);
     if (!rc && (st.host || si.host)) CK(ctx, cudaStreamSynchronize(ctx->stream));
+    return rc;
+}
+
+int modem_gpu_set_phasor(modem_ctx_t* ctx, const modem_phasor_t* ph)
+{
+    if (!ctx) return MODEM_ERR_INVALID;
+    if (!ph || ph->kind == MODEM_PHASOR_TABLE) {
+        ctx->phasor_on = false;
+        return MODEM_OK;
+    }
+    if (ph->struct_size != sizeof(modem_phasor_t)) return fail(ctx, MODEM_ERR_INVALID, "modem_phasor_t size mismatch (ABI)");
+    if (ph->kind > MODEM_PHASOR_DMPSK) return fail(ctx, MODEM_ERR_INVALID, "unknown phasor kind");
+    if (ph->bits_per_symbol != ctx->cfg.bits_per_symbol)
+        return fail(ctx, MODEM_ERR_INVALID, "phasor bits_per_symbol differs from the context's");
+    if (ph->kind == MODEM_PHASOR_BFSK && ph->bits_per_symbol != 1) return fail(ctx, MODEM_ERR_INVALID, "bfsk carries 1 bit per symbol (bfsk.rs:33)");
+    if (ph->kind == MODEM_PHASOR_MSK) {
+        if (ph->bits_per_symbol != 2) return fail(ctx, MODEM_ERR_INVALID, "msk carries 2 bits per symbol (msk.rs:27)");
+        if (ctx->cfg.samples_per_symbol % 2) return fail(ctx, MODEM_ERR_INVALID, "assertion failed: samples_per_symbol % 2 == 0 (msk.rs:13)");
+    } else if (ctx->cfg.q_offset) {
+        return fail(ctx, MODEM_ERR_INVALID, "q_offset (EvenOddOffset) is only defined for 2-bit memoryless mappers and msk");
+    }
+    ctx->phasor = *ph;
+    ctx->phasor_on = true;
+    return MODEM_OK;
+}
+
+int modem_gpu_preamble(modem_ctx_t* ctx, size_t F, size_t n, float amplitude, modem_c32_t* tx)
+{
+    if (!ctx || (!tx && F && n)) return fail(ctx, MODEM_ERR_INVALID, "preamble: null argument");
+    CK(ctx, cudaSetDevice(ctx->device));
+    if (F == 0 || n == 0) return MODEM_OK;
+    Staged st;
+    int rc = stage_out(ctx, ctx->s_tx, tx, F * n * sizeof(float2), &st);
+    if (rc) return rc;
+    const unsigned blocks = (unsigned)std::min<u64>(((u64)F * n + mg::kThreads - 1) / mg::kThreads, (u64)ctx->sm_count * 16);
+    mg::tone_kernel<<<blocks, mg::kThreads, 0, ctx->stream>>>((float2*)st.dev, nullptr, 0, F, n, amplitude, channel_view(ctx), ctx->cfg.sample0);
+    ctx->launches++;
+    CK(ctx, cudaGetLastError());
+    rc = finish_out(ctx, st);
+    if (!rc && st.host) CK(ctx, cudaStreamSynchronize(ctx->stream));
+    return rc;
+}
+
+int modem_gpu_modulate_real(modem_ctx_t* ctx, const uint8_t* bits, size_t F, size_t nbits, size_t preamble,
+                            float preamble_amplitude, float* out)
+{
+    if (!ctx || (!bits && F && nbits) || !out) return fail(ctx, MODEM_ERR_INVALID, "modulate_real: null argument");
+    CK(ctx, cudaSetDevice(ctx->device));
+    if (ctx->n_channels && F > ctx->n_channels * ctx->frames_per_channel)
+        return fail(ctx, MODEM_ERR_INVALID, "modulate_real: more frames than channels * frames_per_channel");
+    const size_t L = modem_gpu_frame_samples(ctx, nbits);
+    const size_t row = preamble + L;
+    if (F == 0 || row == 0) return MODEM_OK;
+    Staged sb, so;
+    int rc = stage_in(ctx, ctx->s_bits, bits, F * nbits, &sb);
+    if (!rc) rc = stage_out(ctx, ctx->s_re, out, F * row * sizeof(float), &so);
+    if (rc) return rc;
+    if (preamble) {
+        const unsigned blocks = (unsigned)std::min<u64>(((u64)F * preamble + mg::kThreads - 1) / mg::kThreads, (u64)ctx->sm_count * 16);
+        mg::tone_kernel<<<blocks, mg::kThreads, 0, ctx->stream>>>(nullptr, (float*)so.dev, row, F, preamble, preamble_amplitude,
+                                                                 channel_view(ctx), ctx->cfg.sample0);
+        ctx->launches++;
+        CK(ctx, cudaGetLastError());
+    }
+    RealOut ro;
+    ro.re = (float*)so.dev;
+    ro.stride = row;
+    ro.offset = preamble;
+    ro.sample_skip = preamble;
+    rc = launch_tx(ctx, (const uint8_t*)sb.dev, F, nbits, nullptr, nullptr, &ro);
+    if (!rc) rc = finish_out(ctx, so);
+    if (!rc && so.host) CK(ctx, cudaStreamSynchronize(ctx->stream));
+    return rc;
+}
+
+int modem_gpu_lock_phase(modem_ctx_t* ctx, const void* samples, uint32_t fmt, size_t F, size_t L, const float* hilbert_taps,
+                         size_t n_hilbert, size_t lock_samples, float* phase_offset)
+{
+    if (!ctx || (!samples && F && L) || !phase_offset) return fail(ctx, MODEM_ERR_INVALID, "lock_phase: null argument");
+    if (fmt > MODEM_SAMPLES_I16) return fail(ctx, MODEM_ERR_INVALID, "lock_phase: unknown sample format");
+    if (L < lock_samples) return fail(ctx, MODEM_ERR_INVALID, "lock_phase: called `Option::unwrap()` on a `None` value (fewer samples than the lock needs, demodulator.rs:34)");
+    CK(ctx, cudaSetDevice(ctx->device));
+    if (F == 0) return MODEM_OK;
+    Staged sr, sp;
+    /* only the first lock_samples of each row are needed, but rows are contiguous: stage the lot */
+    int rc = stage_in(ctx, ctx->s_raw, samples, F * L * sample_bytes(fmt), &sr);
+    if (!rc) rc = stage_out(ctx, ctx->s_po, phase_offset, F * sizeof(float), &sp);
+    if (!rc) rc = launch_lock(ctx, sr.dev, fmt, F, L, hilbert_taps, n_hilbert, lock_samples, (float*)sp.dev);
+    if (!rc) rc = finish_out(ctx, sp);
+    if (!rc && sp.host) CK(ctx, cudaStreamSynchronize(ctx->stream));
+    return rc;
+}
+
+int modem_gpu_demodulate_real(modem_ctx_t* ctx, const void* samples, uint32_t fmt, size_t F, size_t L, size_t lock_samples,
+                              const float* hilbert_taps, size_t n_hilbert, float* phase_offset, uint8_t* sym, uint8_t* bits,
+                              modem_c32_t* soft, modem_c32_t* filt)
+{
+    if (!ctx || (!samples && F && L)) return fail(ctx, MODEM_ERR_INVALID, "demodulate_real: null argument");
+    if (fmt > MODEM_SAMPLES_I16) return fail(ctx, MODEM_ERR_INVALID, "demodulate_real: unknown sample format");
+    if (L < lock_samples) return fail(ctx, MODEM_ERR_INVALID, "demodulate_real: called `Option::unwrap()` on a `None` value (fewer samples than the lock needs, demodulator.rs:34)");
+    CK(ctx, cudaSetDevice(ctx->device));
+    if (ctx->n_channels && F > ctx->n_channels * ctx->frames_per_channel)
+        return fail(ctx, MODEM_ERR_INVALID, "demodulate_real: more frames than channels * frames_per_channel");
+    if (F == 0) return MODEM_OK;
+    const size_t Lr = L - lock_samples;
+    const size_t K = modem_gpu_decided_symbols(ctx, Lr);
+    const size_t bps = ctx->cfg.bits_per_symbol;
+    Staged sr, sp, ss, sb, so, sf;
+    int rc = stage_in(ctx, ctx->s_raw, samples, F * L * sample_bytes(fmt), &sr);
+    float* d_po = nullptr;
+    if (!rc && lock_samples) {
+        if (phase_offset) {
+            rc = stage_out(ctx, ctx->s_po, phase_offset, F * sizeof(float), &sp);
+            d_po = (float*)sp.dev;
+        } else {
+            rc = ensure(ctx, ctx->s_po, F * sizeof(float));
+            d_po = (float*)ctx->s_po.p;
+        }
+        if (!rc) rc = launch_lock(ctx, sr.dev, fmt, F, L, hilbert_taps, n_hilbert, lock_samples, d_po);
+    }
+    if (!rc) rc = stage_out(ctx, ctx->s_sym, sym, F * K, &ss);
+    if (!rc) rc = stage_out(ctx, ctx->s_bits_out, bits, F * K * bps, &sb);
+    if (!rc) rc = stage_out(ctx, ctx->s_soft, soft, F * K * sizeof(float2), &so);
+    if (!rc) rc = stage_out(ctx, ctx->s_filt, filt, F * Lr * sizeof(float2), &sf);
+    if (!rc && Lr) {
+        RawSrc src;
+        src.raw = sr.dev;
+        src.fmt = fmt;
+        src.stride = L;
+        src.skip = lock_samples;
+        src.d_po = d_po;
+        if (fmt == MODEM_SAMPLES_C32) src.fmt = 3; /* analytic rows supplied by the caller: Demodulator::next reads .re */
+        rc = launch_rx(ctx, nullptr, F, Lr, (uint8_t*)ss.dev, (uint8_t*)sb.dev, (float2*)so.dev, (float2*)sf.dev, nullptr, 0, nullptr,
+                       0.0f, 0, 0, &src);
+    }
+    if (!rc) rc = finish_out(ctx, sp);
+    if (!rc) rc = finish_out(ctx, ss);
+    if (!rc) rc = finish_out(ctx, sb);
+    if (!rc) rc = finish_out(ctx, so);
+    if (!rc) rc = finish_out(ctx, sf);
+    if (!rc && (sp.host || ss.host || sb.host || so.host || sf.host)) CK(ctx, cudaStreamSynchronize(ctx->stream));
     return rc;
 }
 

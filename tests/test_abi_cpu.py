@@ -20,10 +20,10 @@ def _declared_symbols():
 def test_library_exports_every_declared_symbol(pkg):
     L = pkg.lib()
     names = _declared_symbols()
-    assert len(names) >= 35
+    assert len(names) >= 42
     missing = [n for n in names if not hasattr(L, n)]
     assert not missing, missing
-    assert L.modem_gpu_abi_version() == 1
+    assert L.modem_gpu_abi_version() == 2
 
 
 def test_cfg_struct_matches_header(pkg):
@@ -68,6 +68,34 @@ def test_invalid_modulation_name(pkg):
     for bad in ["nope", "bfsk", "msk", "dqpsk"]:
         with pytest.raises(pkg.ModemError):
             pkg.host_constellation(bad)
+
+
+def test_host_phasor_by_name(pkg, orc):
+    """The stateful -m rows of modulate.rs:74-95: same constructor constants as the oracle's phasors."""
+    L = orc.lib()
+    for name, kind in [("bfsk", pkg.capi.PHASOR_BFSK), ("mfsk", pkg.capi.PHASOR_MFSK), ("16cpfsk", pkg.capi.PHASOR_CPFSK),
+                       ("msk", pkg.capi.PHASOR_MSK), ("dqpsk", pkg.capi.PHASOR_DMPSK), ("dbpsk", pkg.capi.PHASOR_DMPSK)]:
+        ph, bps, evenodd = pkg.host_phasor(name, 1250, 10000)
+        o = orc.Phasor()
+        assert L.orc_phasor_by_name(C.byref(o), name.encode(), 1250, 10000) == 1
+        assert ph.kind == kind and bps == o.bits_per_symbol == ph.bits_per_symbol
+        assert evenodd == (name == "msk")
+        assert np.float32(ph.amplitude) == np.float32(o.amplitude)
+        if name in ("bfsk", "mfsk", "16cpfsk"):
+            assert np.float32(ph.deviation).view(np.uint32) == np.float32(o.deviation).view(np.uint32)
+        if name in ("dqpsk", "dbpsk"):
+            assert np.float32(ph.phase) == np.float32(o.phase) and np.float32(ph.shift) == np.float32(o.shift)
+    assert C.sizeof(pkg.Phasor) == 32
+    with pytest.raises(pkg.ModemError):
+        pkg.host_phasor("qpsk", 1250, 10000)
+    with pytest.raises(pkg.ModemError):
+        pkg.host_phasor("msk", 3333, 10000)  # sps 3: msk.rs:13 assert
+
+
+def test_hilbert_taps_equal_oracle(pkg, orc):
+    h = pkg.hilbert_taps()
+    assert len(h) == 23 and np.array_equal(h, orc.hilbert_taps())
+    assert h[11] == 0.0 and h[10] == np.float32(-0.62794) and h[12] == np.float32(0.62794)  # demodulate.rs:58-60
 
 
 def test_apsk_ring_verification(pkg):
