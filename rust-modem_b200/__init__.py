@@ -7,6 +7,7 @@ is loaded with `__graft_entry__.load_package()` (importlib) under the module nam
 `rust_modem_b200`.  There is no CPU fallback: without the built library or without an
 sm_100 GPU every compute call raises.
 """
+from . import capi
 from .capi import (ModemError, Modem, ModemCfg, lib, build_library, library_path, host_constellation,
                    lowpass_taps, rrc_taps, hilbert_taps, host_phasor, Phasor, sample_freq, samples_per_symbol, FLAG_FUSED_MAC,
                    STATEFUL_NAMES)

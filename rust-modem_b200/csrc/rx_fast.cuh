@@ -272,8 +272,7 @@ __global__ void __launch_bounds__(THREADS, MINB)
                 if (it * THREADS + tid < C::NCHUNK) {
                     float n0 = 0.0f, n1 = 0.0f;
                     const bool v0 = n >= vlo_n && n < vhi_n, v1 = v0;
-                    if (v0) n0 = noise_re(a.nz, gf, (u64)n);
-                    if (v1) n1 = noise_re(a.nz, gf, (u64)(n + 1));
+                    if (v0) noise_re_pair(a.nz, gf, (u64)n, &n0, &n1); /* n is even: one Philox block per pair */
                     /* xr[] must be indexed statically to stay in registers */
 #pragma unroll
                     for (int j = 0; j < C::ITER; ++j)
@@ -469,12 +468,12 @@ cudaError_t rx_fast_launch_t(const RxArgs& a, const float* h_taps, cudaStream_t 
 }
 
 /* all (OFF, FMA, NOISE) combinations of one (NT, THREADS, MINB) */
-template <int NT, int THREADS, int MINB, int R>
+template <int NT, int THREADS, int MINB, int R, int PF = RX_DEFAULT_PF, int TMC = RX_DEFAULT_TMC>
 cudaError_t rx_fast_dispatch(const RxArgs& a, const float* h_taps, bool fma, cudaStream_t stream)
 {
     const bool odd = (a.delay & 1u) != 0; /* OFF = 0 for odd delay, 1 for even */
     const bool noise = a.nz.sigma != 0.0f;
-#define MG_RX_CASE(O, F, N) return rx_fast_launch_t<NT, O, F, N, THREADS, MINB, R>(a, h_taps, stream)
+#define MG_RX_CASE(O, F, N) return rx_fast_launch_t<NT, O, F, N, THREADS, MINB, R, PF, TMC>(a, h_taps, stream)
     if (odd) {
         if (fma) { if (noise) MG_RX_CASE(0, true, true); else MG_RX_CASE(0, true, false); }
         else     { if (noise) MG_RX_CASE(0, false, true); else MG_RX_CASE(0, false, false); }

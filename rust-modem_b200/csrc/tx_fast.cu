@@ -2,6 +2,8 @@
  * tx_fast.cu -- compile-time specialised TX kernels (rectangular hold with word-wise bit
  * loads; 129-tap pulse shaping at 8 samples per symbol) and their launchers.
  */
+#include <stdlib.h>
+
 #include "launch.h"
 
 namespace mg {
@@ -82,21 +84,26 @@ __global__ void __launch_bounds__(kThreads, 4) tx_rect_fast_kernel(const __grid_
 }
 
 /*
- * Fast pulse-shaped TX for compile-time (SPS, NT): one thread owns one symbol period
- * (SPS consecutive samples).  The J = ceil(NT/SPS) symbols that reach it sit in registers,
- * the taps are kernel-parameter constants (constant-bank operands, no load instructions),
- * and the CTA's 2 KB-per-warp output is transposed through shared memory so that global
- * stores are full 128-bit coalesced.
+ * Fast pulse-shaped TX for compile-time (SPS, NT): one thread owns one symbol period (SPS consecutive
+ * samples) of FB frames at a time.  The taps are kernel-parameter constants: each (h, h) pair is ONE 64-bit
+ * uniform-register operand fetched from the constant bank, and it feeds the MACs of all FB frames before the
+ * next one is fetched (with one frame per fetch the uniform loads cost more issue slots than the MACs:
+ * 84 thread-instructions per sample in profiles/r01, 2/3 of them LDCU/UMOV).  The walk is symbol-major: the
+ * J = ceil(NT/SPS) symbols that reach the period are read one at a time from shared memory (one 64-bit
+ * conflict-free load per frame) and each feeds the SPS phase accumulators with taps p + j*SPS, so every
+ * accumulator still sees its taps in ascending order (fir.rs:21-24; the zero-stuffed terms are exact no-ops).
+ * The CTA's 2 KB-per-warp output is transposed through shared memory so global stores are 128-bit coalesced.
  */
-template <int SPS, int NT, bool FMA>
-__global__ void __launch_bounds__(kThreads)
+template <int SPS, int NT, bool FMA, int FB>
+__global__ void __launch_bounds__(kThreads, FB >= 4 ? 2 : 3)
     tx_shaped_fast_kernel(const __grid_constant__ TxArgs a, const __grid_constant__ TapsParam<NT> taps)
 {
     static_assert(SPS == 8, "output transpose below is written for 8 samples per symbol");
     constexpr int J = (NT + SPS - 1) / SPS; /* symbols reaching one output */
     constexpr int HALO = J - 1;
+    constexpr int ROW = kThreads + HALO;
     __shared__ float2 s_lut[kMaxLut];
-    __shared__ __align__(8) float2 s_sym[2][kThreads + HALO];
+    __shared__ __align__(8) float2 s_sym[2][FB][ROW];
     __shared__ __align__(16) float4 s_out[kThreads / 32][32 * SPS / 2]; /* per warp: 32 symbols x 8 samples x 8 B */
 
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -122,14 +129,18 @@ __global__ void __launch_bounds__(kThreads)
         for (int p = 0; p < SPS; ++p) mg_sincosf(nco_phase(w, a.sample0 + m * SPS + p), &sn[p], &cs[p]);
     }
 
-    auto stage = [&](int buf, u64 f) {
-        const uint8_t* fb = a.bits + f * a.nbits;
-        for (int i = tid; i < kThreads + HALO; i += kThreads) {
-            long long mm = (long long)k0 - HALO + i;
-            float2 v = make_float2(0.0f, 0.0f);
-            if (mm >= 0 && (u64)mm < a.nsym)
-                v = s_lut[((u64)mm % a.n_tables) * a.n_const + sym_index_plain(fb, (u64)mm, a.bps)];
-            s_sym[buf][i] = v;
+    /* mapped symbols of FB frames: s_sym[buf][g][i] = (i, q) of symbol k0 - HALO + i of frame fg + g */
+    auto stage = [&](int buf, u64 fg) {
+        for (int i = tid; i < ROW; i += kThreads) {
+            const long long mm = (long long)k0 - HALO + i;
+            const bool in = mm >= 0 && (u64)mm < a.nsym;
+            const uint32_t toff = in ? (uint32_t)((u64)mm % a.n_tables) * a.n_const : 0u;
+#pragma unroll
+            for (int g = 0; g < FB; ++g) {
+                float2 v = make_float2(0.0f, 0.0f);
+                if (in && fg + g < f1) v = s_lut[toff + sym_index_plain(a.bits + (fg + g) * a.nbits, (u64)mm, a.bps)];
+                s_sym[buf][g][i] = v;
+            }
         }
     };
     __syncthreads();
@@ -137,44 +148,56 @@ __global__ void __launch_bounds__(kThreads)
     __syncthreads();
 
     int buf = 0;
-    for (u64 f = f0; f < f1; ++f, buf ^= 1) {
-        if (f + 1 < f1) stage(buf ^ 1, f + 1); /* overlap next frame's symbol fetch */
-        f32x2 win[J]; /* (i, q) of symbol m - j as one packed pair */
+    for (u64 fg = f0; fg < f1; fg += FB, buf ^= 1) {
+        if (fg + FB < f1) stage(buf ^ 1, fg + FB); /* overlap the next group's symbol fetch */
+        f32x2 acc[FB][SPS];
 #pragma unroll
-        for (int j = 0; j < J; ++j) win[j] = reinterpret_cast<const f32x2*>(s_sym[buf])[tid + HALO - j];
+        for (int g = 0; g < FB; ++g)
+#pragma unroll
+            for (int p = 0; p < SPS; ++p) acc[g][p] = 0ull; /* (+0.0f, +0.0f) */
+#pragma unroll
+        for (int j = 0; j < J; ++j) {
+            f32x2 win[FB]; /* (i, q) of symbol m - j, one packed pair per frame */
+#pragma unroll
+            for (int g = 0; g < FB; ++g) win[g] = reinterpret_cast<const f32x2*>(s_sym[buf][g])[tid + HALO - j];
+#pragma unroll
+            for (int p = 0; p < SPS; ++p) {
+                if (p + j * SPS < NT) {
+                    const f32x2 hh = pk2(taps.hh[p + j * SPS].x, taps.hh[p + j * SPS].y);
+#pragma unroll
+                    for (int g = 0; g < FB; ++g) acc[g][p] = mac2<FMA>(acc[g][p], win[g], hh, one);
+                }
+            }
+        }
 
         float4* wout = s_out[wid];
-#pragma unroll
-        for (int pp = 0; pp < SPS; pp += 2) {
-            float2 o[2];
-#pragma unroll
-            for (int e = 0; e < 2; ++e) {
-                const int p = pp + e;
-                f32x2 acc = 0ull; /* (+0.0f, +0.0f) */
-#pragma unroll
-                for (int j = 0; j < J; ++j) {
-                    if (p + j * SPS < NT)
-                        acc = mac2<FMA>(acc, win[j], pk2(taps.hh[p + j * SPS].x, taps.hh[p + j * SPS].y), one);
-                }
-                const float2 bb = unpk2(acc);
-                o[e] = mix_iq(bb.x, bb.y, cs[p], sn[p]);
-            }
-            /* chunk c = pp/2 of row `lane` (4 chunks of 16 B per row), XOR-swizzled */
-            const int c = pp >> 1;
-            wout[lane * 4 + (c ^ ((lane >> 1) & 3))] = make_float4(o[0].x, o[0].y, o[1].x, o[1].y);
-        }
-        __syncwarp();
-        /* coalesced write-out of this warp's 32 symbols = 256 samples = 128 float4 */
         const u64 sym_w0 = k0 + (u64)wid * 32;
-        float4* gout = reinterpret_cast<float4*>(a.tx + f * a.L + sym_w0 * SPS);
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const int g = lane + 32 * i; /* linear 16-byte chunk in the warp tile */
-            const int row = g >> 2, c = g & 3;
-            float4 v = wout[row * 4 + (c ^ ((row >> 1) & 3))];
-            if (sym_w0 + row < a.nsym) __stcs(gout + g, v);
+        for (int g = 0; g < FB; ++g) {
+            if (fg + g < f1) { /* uniform across the CTA */
+#pragma unroll
+                for (int pp = 0; pp < SPS; pp += 2) {
+                    const float2 b0 = unpk2(acc[g][pp]), b1 = unpk2(acc[g][pp + 1]);
+                    const float2 o0 = mix_iq(b0.x, b0.y, cs[pp], sn[pp]);
+                    const float2 o1 = mix_iq(b1.x, b1.y, cs[pp + 1], sn[pp + 1]);
+                    /* chunk c = pp/2 of row `lane` (4 chunks of 16 B per row), XOR-swizzled */
+                    const int c = pp >> 1;
+                    wout[lane * 4 + (c ^ ((lane >> 1) & 3))] = make_float4(o0.x, o0.y, o1.x, o1.y);
+                }
+                __syncwarp();
+                /* coalesced write-out of this warp's 32 symbols = 256 samples = 128 float4 */
+                float4* gout = reinterpret_cast<float4*>(a.tx + (fg + g) * a.L + sym_w0 * SPS);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int q = lane + 32 * i; /* linear 16-byte chunk in the warp tile */
+                    const int row = q >> 2, c = q & 3;
+                    const float4 v = wout[row * 4 + (c ^ ((row >> 1) & 3))];
+                    if (sym_w0 + row < a.nsym) __stcs(gout + q, v);
+                }
+                __syncwarp();
+            }
         }
-        __syncthreads(); /* s_sym[buf^1] staged, s_out reusable */
+        __syncthreads(); /* s_sym[buf^1] staged, s_sym[buf] free for the group after next */
     }
 }
 
@@ -199,8 +222,14 @@ cudaError_t tx_shaped_fast_launch(const TxArgs& a, const float* h_taps, bool fma
 {
     dim3 grid((unsigned)tx_shaped_fast_tiles(a.nsym), (unsigned)((a.F + a.frames_per_block - 1) / a.frames_per_block));
     const TapsParam<129> tp = make_taps_param<129>(h_taps);
-    if (fma) tx_shaped_fast_kernel<8, 129, true><<<grid, kThreads, 0, stream>>>(a, tp);
-    else tx_shaped_fast_kernel<8, 129, false><<<grid, kThreads, 0, stream>>>(a, tp);
+    static const int fb = getenv("MODEM_GPU_TX_FB") ? atoi(getenv("MODEM_GPU_TX_FB")) : 2; /* tuning knob: 2 measured best (exact 3.24 ms, fused 2.58 ms at C3; 4: 3.65 / 2.99) */
+    if (fb != 4) {
+        if (fma) tx_shaped_fast_kernel<8, 129, true, 2><<<grid, kThreads, 0, stream>>>(a, tp);
+        else tx_shaped_fast_kernel<8, 129, false, 2><<<grid, kThreads, 0, stream>>>(a, tp);
+    } else {
+        if (fma) tx_shaped_fast_kernel<8, 129, true, 4><<<grid, kThreads, 0, stream>>>(a, tp);
+        else tx_shaped_fast_kernel<8, 129, false, 4><<<grid, kThreads, 0, stream>>>(a, tp);
+    }
     return cudaGetLastError();
 }
 

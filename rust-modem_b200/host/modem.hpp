@@ -12,6 +12,10 @@
  *   modem::data::{Source, SourceUpdate, Bits, EvenOddOffset}               data.rs
  *   modem::digital::{DigitalPhasor, bask::BASK, bpsk::BPSK, qpsk::QPSK, qam::QAM, mpsk::MPSK,
  *                    oqpsk::OQPSK, dcqpsk::DCQPSK, apsk::{APSK, Ring}}   digital/<scheme>.rs
+ *   modem::digital::{bfsk::BFSK, mfsk::{MFSK, DefaultMap, IncreaseMap}, cpfsk::CPFSK, msk::MSK,
+ *                    dmpsk::DMPSK}                                       the stateful schemes (TX)
+ *   modem::data::AsciiBits                                                 data.rs:125-186
+ *   modem::phasor::{Phasor, Raw}, modem::modulator::Modulator              phasor.rs, modulator.rs:8-62
  *   modem::modulator::{IQSample, DigitalModulator}                        modulator.rs
  *   modem::demodulator::Demodulator                                        demodulator.rs
  *
@@ -30,6 +34,10 @@
 #include <cstdint>
 #include <cstring>
 #include <functional>
+#include <charconv>
+#include <istream>
+#include <iterator>
+#include <type_traits>
 #include <memory>
 #include <optional>
 #include <stdexcept>
@@ -94,6 +102,13 @@ inline FIRFilter lowpass()
 {
     size_t n = 0;
     const float* p = modem_lowpass_taps(&n);
+    return FIRFilter(p, n);
+}
+/* src/bin/demodulate.rs:47-75 */
+inline FIRFilter hilbert()
+{
+    size_t n = 0;
+    const float* p = modem_hilbert_taps(&n);
     return FIRFilter(p, n);
 }
 } // namespace fir
@@ -182,6 +197,71 @@ public:
     size_t q_offset() const override { return q_off_; }
     D& inner() { return data_; }
 };
+/* type-erased form used by src/bin/modulate.rs:101-107 (`Box<data::Source>` around any inner source) */
+class EvenOddOffsetBoxed : public Source {
+    std::unique_ptr<Source> data_;
+    SymbolClock clock_;
+    uint8_t cur_[2] = {0, 0};
+    size_t q_off_;
+public:
+    EvenOddOffsetBoxed(std::unique_ptr<Source> d, size_t samples_per_symbol, size_t bits_per_symbol)
+        : data_(std::move(d)), clock_(samples_per_symbol / (bits_per_symbol ? bits_per_symbol : 1)), q_off_(samples_per_symbol / 2)
+    {
+        if (bits_per_symbol != 2) throw Panic("assertion failed: bits_per_symbol == 2");
+        if (samples_per_symbol % bits_per_symbol) throw Panic("assertion failed: samples_per_symbol % bits_per_symbol == 0");
+    }
+    SourceUpdate next() override
+    {
+        SourceUpdate in = data_->next();
+        if (in.kind == SourceUpdate::Finished) return in;
+        if (in.kind == SourceUpdate::Changed) {
+            clock_.next();
+            cur_[0] = in.bits[0];
+            return SourceUpdate{SourceUpdate::Changed, cur_, 2};
+        }
+        if (clock_.next()) {
+            cur_[1] = in.bits[1];
+            return SourceUpdate{SourceUpdate::Changed, cur_, 2};
+        }
+        return SourceUpdate{SourceUpdate::Unchanged, cur_, 2};
+    }
+    size_t q_offset() const override { return q_off_; }
+};
+/* data.rs:125-186: ASCII '0'/'1' characters from a stream, whitespace skipped, anything else panics */
+class AsciiBits : public Source {
+    std::istream& stream_;
+    SymbolClock clock_;
+    std::vector<uint8_t> bits_;
+    bool next_bit(uint8_t* out) /* data.rs:143-162 */
+    {
+        for (;;) {
+            const int c = stream_.get();
+            if (c == std::char_traits<char>::eof()) return false;
+            /* char::is_whitespace for a byte value (White_Space property, U+0000..U+00FF) */
+            if (c == ' ' || (c >= 0x09 && c <= 0x0d) || c == 0x85 || c == 0xa0) continue;
+            if (c != '0' && c != '1') throw Panic("assertion failed: (bit as char).is_digit(2)"); /* data.rs:158 */
+            *out = (uint8_t)(c - '0');
+            return true;
+        }
+    }
+    bool read_bits() /* data.rs:164-174 */
+    {
+        for (auto& b : bits_)
+            if (!next_bit(&b)) return false;
+        return true;
+    }
+public:
+    AsciiBits(std::istream& stream, size_t samples_per_symbol, size_t bits_per_symbol)
+        : stream_(stream), clock_(samples_per_symbol), bits_(bits_per_symbol, 0) {}
+    SourceUpdate next() override /* data.rs:177-189 */
+    {
+        if (clock_.next()) {
+            if (read_bits()) return SourceUpdate{SourceUpdate::Changed, bits_.data(), bits_.size()};
+            return SourceUpdate{SourceUpdate::Finished, nullptr, 0};
+        }
+        return SourceUpdate{SourceUpdate::Unchanged, bits_.data(), bits_.size()};
+    }
+};
 } // namespace data
 
 /* ------------------------------------------------------------------ digital/ */
@@ -192,6 +272,10 @@ struct DigitalPhasor { /* digital/phasor.rs:1-12 */
     /* constellation: n_tables() * 2^bps (i,q) pairs; symbol k uses table k % n_tables() (dcqpsk's update()) */
     virtual size_t n_tables() const { return 1; }
     virtual void table(float* out_iq) const = 0;
+    /* stateful / time-varying schemes (update() or a sample-dependent i()/q()): evaluated by the phasor
+     * kernels from this parameter block instead of a table */
+    virtual bool stateful() const { return false; }
+    virtual modem_phasor_t phasor_params() const { return modem_phasor_t{}; }
     /* i()/q() of the reference, served from the table (s is ignored by every memoryless scheme) */
     std::pair<float, float> next(size_t /*s*/, const uint8_t* b, size_t symbol_index = 0) const
     {
@@ -314,6 +398,91 @@ inline std::unique_ptr<DigitalPhasor> by_name(const std::string& dmod)
         return std::make_unique<apsk::APSK>(A, 4, std::vector<apsk::Ring>{apsk::Ring(0, 4, 0.5f, PI / 4.0f), apsk::Ring(4, 16, 1.0f, PI / 12.0f)});
     throw Panic("invalid digital modulation"); /* modulate.rs:94 */
 }
+/* ---- the stateful schemes (TX only: the reference has no receiver for them) ---- */
+struct StatefulPhasor : DigitalPhasor {
+    modem_phasor_t p{};
+    StatefulPhasor() { p.struct_size = sizeof p; }
+    size_t bits_per_symbol() const override { return p.bits_per_symbol; }
+    bool stateful() const override { return true; }
+    modem_phasor_t phasor_params() const override { return p; }
+    void table(float* o) const override { std::memset(o, 0, sizeof(float) * 2 * ((size_t)1 << p.bits_per_symbol)); }
+};
+namespace bfsk {
+struct BFSK : StatefulPhasor { /* bfsk.rs:14-21 */
+    BFSK(const freq::Freq& d, float a)
+    {
+        p.kind = MODEM_PHASOR_BFSK;
+        p.bits_per_symbol = 1;
+        p.deviation = d.sample_freq();
+        p.amplitude = a;
+    }
+};
+} // namespace bfsk
+namespace mfsk {
+struct DefaultMap {};  /* mfsk.rs:11-27 */
+struct IncreaseMap {}; /* mfsk.rs:29-35 */
+struct MFSK : StatefulPhasor { /* mfsk.rs:47-58 */
+    MFSK(size_t bits_per_symbol, const freq::Freq& deviation, float amplitude, IncreaseMap) { init(bits_per_symbol, deviation, amplitude, 1); }
+    MFSK(size_t bits_per_symbol, const freq::Freq& deviation, float amplitude, DefaultMap) { init(bits_per_symbol, deviation, amplitude, 0); }
+private:
+    void init(size_t bps, const freq::Freq& d, float a, uint32_t inc)
+    {
+        p.kind = MODEM_PHASOR_MFSK;
+        p.bits_per_symbol = (uint32_t)bps;
+        p.deviation = d.sample_freq();
+        p.amplitude = a;
+        p.mfsk_increase_map = inc;
+    }
+};
+} // namespace mfsk
+namespace cpfsk {
+struct CPFSK : StatefulPhasor { /* cpfsk.rs:14-23 */
+    CPFSK(size_t bits_per_symbol, const rates::Rates& r, float amplitude, size_t deviation)
+    {
+        p.kind = MODEM_PHASOR_CPFSK;
+        p.bits_per_symbol = (uint32_t)bits_per_symbol;
+        p.deviation = freq::Freq(deviation * r.baud_rate / 2, r.sample_rate).sample_freq();
+        p.amplitude = amplitude;
+    }
+};
+} // namespace cpfsk
+namespace msk {
+struct MSK : StatefulPhasor { /* msk.rs:12-19 */
+    MSK(float amplitude, size_t samples_per_symbol)
+    {
+        if (samples_per_symbol % 2) throw Panic("assertion failed: samples_per_symbol % 2 == 0"); /* msk.rs:13 */
+        p.kind = MODEM_PHASOR_MSK;
+        p.bits_per_symbol = 2;
+        p.amplitude = amplitude;
+    }
+};
+} // namespace msk
+namespace dmpsk {
+struct DMPSK : StatefulPhasor { /* dmpsk.rs:16-23 */
+    DMPSK(size_t bits_per_symbol, float amplitude, float phase, float shift)
+    {
+        p.kind = MODEM_PHASOR_DMPSK;
+        p.bits_per_symbol = (uint32_t)bits_per_symbol;
+        p.amplitude = amplitude;
+        p.phase = phase;
+        p.shift = shift;
+    }
+};
+} // namespace dmpsk
+
+/* every `-m` name of src/bin/modulate.rs:74-95 */
+inline std::unique_ptr<DigitalPhasor> by_name(const std::string& dmod, const rates::Rates& rates)
+{
+    const float A = 1.0f, PI = 3.14159265358979323846264338327950288f;
+    const size_t sr = rates.sample_rate;
+    if (dmod == "bfsk") return std::make_unique<bfsk::BFSK>(freq::Freq(200, sr), A);
+    if (dmod == "msk") return std::make_unique<msk::MSK>(A, rates.samples_per_symbol);
+    if (dmod == "mfsk") return std::make_unique<mfsk::MFSK>(4, freq::Freq(50, sr), A, mfsk::IncreaseMap{});
+    if (dmod == "16cpfsk") return std::make_unique<cpfsk::CPFSK>(4, rates, A, 1);
+    if (dmod == "dqpsk") return std::make_unique<dmpsk::DMPSK>(2, A, PI / 4.0f, PI / 2.0f);
+    if (dmod == "dbpsk") return std::make_unique<dmpsk::DMPSK>(1, A, PI / 4.0f, PI);
+    return by_name(dmod);
+}
 } // namespace digital
 
 /* ------------------------------------------------------------------ gpu: the batched layer L3' */
@@ -362,6 +531,10 @@ public:
         c.slicer_gain = cfg_.slicer_gain;
         c.flags = cfg_.flags;
         check(modem_gpu_create(&ctx_, device, &c), nullptr, "modem_gpu_create");
+        if (phasor.stateful()) {
+            const modem_phasor_t ph = phasor.phasor_params();
+            check(modem_gpu_set_phasor(ctx_, &ph), ctx_, "modem_gpu_set_phasor");
+        }
     }
     ~Context() { modem_gpu_destroy(ctx_); }
     Context(const Context&) = delete;
@@ -390,6 +563,24 @@ struct DemodulatorBatch {
         check(modem_gpu_demodulate(ctx.raw(), rx, F, L, sym, bits, soft, filt, sigma, seed, frame0), ctx.raw(), "modem_gpu_demodulate");
     }
 };
+/* the two binaries' wire-level batch forms (modulate.rs:118-133, demodulate.rs:29-43) */
+struct BinBatch {
+    Context& ctx;
+    explicit BinBatch(Context& c) : ctx(c) {}
+    /* out [F][preamble + L] f32: sync tone then data, real part only */
+    void modulate_real(const uint8_t* bits, size_t F, size_t nbits, size_t preamble, float preamble_amplitude, float* out)
+    {
+        check(modem_gpu_modulate_real(ctx.raw(), bits, F, nbits, preamble, preamble_amplitude, out), ctx.raw(), "modem_gpu_modulate_real");
+    }
+    /* samples [F][L] i16 / f32 real (or complex analytic); filt [F][L - lock] */
+    void demodulate_real(const void* samples, uint32_t fmt, size_t F, size_t L, size_t lock, const fir::FIRFilter* hilbert,
+                         float* phase_offset, uint8_t* sym, uint8_t* bits, Complex32* soft, Complex32* filt)
+    {
+        check(modem_gpu_demodulate_real(ctx.raw(), samples, fmt, F, L, lock, hilbert ? hilbert->coefs : nullptr, hilbert ? hilbert->len : 0,
+                                        phase_offset, sym, bits, soft, filt),
+              ctx.raw(), "modem_gpu_demodulate_real");
+    }
+};
 struct Loopback {
     Context& ctx;
     explicit Loopback(Context& c) : ctx(c) {}
@@ -404,12 +595,71 @@ struct Loopback {
 };
 } // namespace gpu
 
+/* ------------------------------------------------------------------ phasor.rs */
+namespace phasor {
+struct Phasor { /* phasor.rs:1-3 */
+    virtual ~Phasor() = default;
+    virtual std::optional<std::pair<float, float>> next(size_t s) = 0;
+    /* a constant-amplitude tone is what the CUDA path generates; other analog phasors are not on it */
+    virtual bool constant(float* amplitude) const { (void)amplitude; return false; }
+};
+struct Raw : Phasor { /* phasor.rs:5-24 */
+    float amplitude;
+    explicit Raw(float a) : amplitude(a) {}
+    std::optional<std::pair<float, float>> next(size_t) override { return std::make_pair(amplitude, 0.0f); }
+    bool constant(float* a) const override { *a = amplitude; return true; }
+};
+} // namespace phasor
+
 /* ------------------------------------------------------------------ modulator.rs */
 namespace modulator {
 struct IQSample { /* modulator.rs:22-49 */
     float i, q;            /* pub fields read by modulate.rs:111-112 (--iq) */
     Complex32 modulated;   /* what modulate() returns: computed by the TX kernel */
     Complex32 modulate() const { return modulated; } /* modulator.rs:45-48 */
+};
+
+/* Modulator::new(&mut carrier, phasor) -> endless Iterator<Item = IQSample> (modulator.rs:8-20,51-62): the sync
+ * tone of modulate.rs:118-126.  Samples are produced by the tone kernel a block at a time; the borrowed
+ * Carrier's counter advances with every sample handed out, exactly like the reference's per-sample next(). */
+class Modulator {
+    carrier::Carrier& carrier_;
+    std::unique_ptr<phasor::Phasor> phasor_;
+    std::vector<Complex32> buf_;
+    size_t pos_ = 0, block_;
+    float amplitude_ = 0.0f;
+public:
+    Modulator(carrier::Carrier& c, std::unique_ptr<phasor::Phasor> p, size_t block = 4096)
+        : carrier_(c), phasor_(std::move(p)), block_(block)
+    {
+        if (!phasor_->constant(&amplitude_)) throw Panic("Modulator: only phasor::Raw runs on the CUDA path");
+    }
+    std::optional<IQSample> next()
+    {
+        if (pos_ >= buf_.size()) {
+            digital::qpsk::QPSK dummy(0.0f, 1.0f);
+            gpu::PathConfig cfg;
+            cfg.sample_freq = carrier_.sample_freq;
+            cfg.sample0 = carrier_.sample;
+            gpu::Context ctx(dummy, cfg);
+            buf_.resize(block_);
+            check(modem_gpu_preamble(ctx.raw(), 1, block_, amplitude_, buf_.data()), ctx.raw(), "modem_gpu_preamble");
+            pos_ = 0;
+        }
+        carrier_.sample += 1; /* modulator.rs:55 */
+        return IQSample{amplitude_, 0.0f, buf_[pos_++]};
+    }
+    /* `.take(n)`: n samples in one call */
+    std::vector<IQSample> take(size_t n)
+    {
+        std::vector<IQSample> out;
+        out.reserve(n);
+        const size_t keep = block_;
+        if (pos_ >= buf_.size() && n) block_ = n;
+        for (size_t i = 0; i < n; ++i) out.push_back(*next());
+        block_ = keep;
+        return out;
+    }
 };
 
 /* DigitalModulator::new(&mut carrier, phasor, src) -> Iterator<Item = IQSample> (modulator.rs:64-101) */
@@ -508,9 +758,28 @@ class Demodulator {
 public:
     template <class F>
     Demodulator(carrier::Carrier c, S sig, F lp) : carrier_(c), sig_(std::move(sig)), lp_(lp()) {} /* lp is called like the reference's closure */
-    /* PLL phase lock (demodulator.rs:32-36, pll.rs) is a "next" row of the scope table:
-     * the loopback path is coherent, phase_offset stays 0 unless set explicitly. */
-    void lock_phase() { throw Panic("lock_phase: carrier-recovery front end is not on the GPU path yet (SURVEY.md 8f row 2)"); }
+    /* demodulator.rs:32-36: LOCK_SAMPLES analytic samples drive the PLL (pll.rs:16-22) on the GPU; the carrier
+     * counter moves past them */
+    void lock_phase()
+    {
+        std::vector<Complex32> head;
+        for (size_t i = 0; i < LOCK_SAMPLES; ++i) {
+            auto x = sig_();
+            if (!x) throw Panic("called `Option::unwrap()` on a `None` value"); /* demodulator.rs:34 */
+            head.push_back(*x);
+        }
+        digital::qpsk::QPSK dummy(0.0f, 1.0f);
+        gpu::PathConfig cfg;
+        cfg.samples_per_symbol = 1;
+        cfg.sample_freq = carrier_.sample_freq;
+        cfg.sample0 = carrier_.sample;
+        cfg.rx_taps.assign(lp_.coefs, lp_.coefs + lp_.len);
+        gpu::Context ctx(dummy, cfg);
+        check(modem_gpu_lock_phase(ctx.raw(), head.data(), MODEM_SAMPLES_C32, 1, head.size(), nullptr, 0, LOCK_SAMPLES, &phase_offset_),
+              ctx.raw(), "modem_gpu_lock_phase");
+        carrier_.sample += LOCK_SAMPLES;
+    }
+    float phase_offset() const { return phase_offset_; } /* pll.phase_offset */
     void set_phase_offset(float po) { phase_offset_ = po; }
     std::optional<std::pair<float, float>> next()
     {
@@ -520,6 +789,107 @@ public:
         return std::make_pair(v.re, v.im);
     }
 };
+
+/* The composition of src/bin/demodulate.rs:29-41 for a REAL input stream: `input.map(|x| Complex::new(x,
+ * hfir.add(x)))` feeding Demodulator::new(carrier, analytic, lowpass), then lock_phase().  The Hilbert FIR is a
+ * filter description here (the reference evaluates it per sample inside the closure); it runs in the lock
+ * kernel, and one library call does lock + demodulation.  R is a callable returning std::optional<T>, T = int16_t
+ * (`iter_16`, src/bin/util.rs) or float. */
+template <class T>
+class RealDemodulator {
+    static_assert(std::is_same<T, int16_t>::value || std::is_same<T, float>::value, "i16 or f32 samples");
+    carrier::Carrier carrier_;
+    std::vector<T> x_;
+    fir::FIRFilter hilbert_, lp_;
+    bool lock_ = false, started_ = false;
+    float phase_offset_ = 0.0f;
+    std::vector<Complex32> filt_;
+    size_t pos_ = 0;
+    void run()
+    {
+        digital::qpsk::QPSK dummy(0.0f, 1.0f);
+        gpu::PathConfig cfg;
+        cfg.samples_per_symbol = 1;
+        cfg.sample_freq = carrier_.sample_freq;
+        cfg.sample0 = carrier_.sample;
+        cfg.rx_taps.assign(lp_.coefs, lp_.coefs + lp_.len);
+        gpu::Context ctx(dummy, cfg);
+        const size_t lock = lock_ ? LOCK_SAMPLES : 0;
+        if (x_.size() < lock) throw Panic("called `Option::unwrap()` on a `None` value"); /* demodulator.rs:34 */
+        filt_.resize(x_.size() - lock);
+        const uint32_t fmt = std::is_same<T, int16_t>::value ? MODEM_SAMPLES_I16 : MODEM_SAMPLES_F32;
+        gpu::BinBatch(ctx).demodulate_real(x_.data(), fmt, 1, x_.size(), lock, &hilbert_, lock ? &phase_offset_ : nullptr, nullptr, nullptr,
+                                           nullptr, filt_.data());
+        carrier_.sample += x_.size();
+        started_ = true;
+    }
+public:
+    template <class R, class F>
+    RealDemodulator(carrier::Carrier c, R real_sig, fir::FIRFilter hilbert, F lp) : carrier_(c), hilbert_(hilbert), lp_(lp())
+    {
+        while (auto v = real_sig()) x_.push_back(*v);
+    }
+    RealDemodulator(carrier::Carrier c, std::vector<T> samples, fir::FIRFilter hilbert, fir::FIRFilter lp)
+        : carrier_(c), x_(std::move(samples)), hilbert_(hilbert), lp_(lp) {}
+    void lock_phase() { lock_ = true; } /* evaluated with the first next() */
+    float phase_offset()
+    {
+        if (!started_) run();
+        return phase_offset_;
+    }
+    std::optional<std::pair<float, float>> next()
+    {
+        if (!started_) run();
+        if (pos_ >= filt_.size()) return std::nullopt;
+        auto v = filt_[pos_++];
+        return std::make_pair(v.re, v.im);
+    }
+};
 } // namespace demodulator
+
+/* ------------------------------------------------------------------ src/bin helpers */
+namespace bin {
+/* Rust's `{}` for f32 (demodulate.rs:42): the shortest decimal string that round-trips, always positional
+ * (never an exponent), no trailing ".0", "NaN" / "inf" / "-inf". */
+inline std::string display_f32(float v);
+/* src/bin/util.rs:3-37 Read16/Iter16: native-endian i16 words; a trailing odd byte ends the stream */
+inline std::vector<int16_t> read_all_i16(std::istream& in)
+{
+    std::vector<char> raw((std::istreambuf_iterator<char>(in)), std::istreambuf_iterator<char>());
+    std::vector<int16_t> out(raw.size() / 2);
+    if (!out.empty()) std::memcpy(out.data(), raw.data(), out.size() * 2);
+    return out;
+}
+} // namespace bin
+
+inline std::string bin::display_f32(float v)
+{
+    if (std::isnan(v)) return "NaN";
+    if (std::isinf(v)) return v < 0 ? "-inf" : "inf";
+    if (v == 0.0f) return std::signbit(v) ? "-0" : "0";
+    char buf[64];
+    auto r = std::to_chars(buf, buf + sizeof buf, v, std::chars_format::scientific); /* shortest round-trip digits */
+    std::string sci(buf, r.ptr);
+    std::string out;
+    size_t i = 0;
+    if (sci[0] == '-') {
+        out = "-";
+        i = 1;
+    }
+    const size_t e = sci.find('e');
+    std::string digits;
+    for (size_t k = i; k < e; ++k)
+        if (sci[k] != '.') digits.push_back(sci[k]);
+    const int exp10 = std::atoi(sci.c_str() + e + 1); /* value = d.ddd * 10^exp10 */
+    const int nd = (int)digits.size();
+    if (exp10 >= nd - 1) {
+        out += digits + std::string((size_t)(exp10 - (nd - 1)), '0');
+    } else if (exp10 >= 0) {
+        out += digits.substr(0, (size_t)exp10 + 1) + "." + digits.substr((size_t)exp10 + 1);
+    } else {
+        out += "0." + std::string((size_t)(-exp10 - 1), '0') + digits;
+    }
+    return out;
+}
 
 } // namespace modem
