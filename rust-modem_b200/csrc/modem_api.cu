@@ -48,7 +48,16 @@ struct modem_ctx {
     /* stateful phasor (modem_gpu_set_phasor) and the carrier-recovery front end */
     modem_phasor_t phasor{};
     bool phasor_on = false;
-    Scratch s_state, s_re, s_raw, s_po, s_hilbert;
+    Scratch s_state, s_re, s_raw, s_po, s_hilbert, s_siq, s_cptab;
+    struct CpKey { /* what the cpfsk table was built for */
+        u64 L = 0, sample0 = ~0ull;
+        float deviation = 0.0f, amplitude = 0.0f;
+        uint32_t bps = 0;
+        bool operator==(const CpKey& o) const
+        {
+            return L == o.L && sample0 == o.sample0 && deviation == o.deviation && amplitude == o.amplitude && bps == o.bps;
+        }
+    } cp_key;
     /* host-buffer loopback pipeline: three lanes, each with its own stream and chunk buffers */
     struct Lane {
         cudaStream_t s = nullptr;
@@ -486,23 +495,70 @@ int launch_tx_phasor(modem_ctx* ctx, mg::TxArgs& a)
         int rc = ensure(ctx, ctx->s_state, a.F * a.nsym * sizeof(float));
         if (rc) return rc;
         p.state = (const float*)ctx->s_state.p;
-        const unsigned blocks = (unsigned)((a.F + 127) / 128);
-        mg::phasor_scan_kernel<<<blocks, 128, 0, ctx->stream>>>(a.bits, a.nbits, a.F, a.nsym, a.sps, a.sample0, p, (float*)ctx->s_state.p);
+        const unsigned blocks = (unsigned)((a.F + 31) / 32);
+        const size_t rowb = (size_t)mg::kScanChunk * p.bps + 4;
+        const size_t smem = 2 * 32 * rowb + 2 * 32 * (mg::kScanChunk + 1) * sizeof(float);
+        const int aligned4 = (a.nbits % 4 == 0) && ((reinterpret_cast<uintptr_t>(a.bits) & 3u) == 0);
+        float* d_state = (float*)ctx->s_state.p;
+#define MG_SCAN(K)                                                                                                          \
+    do {                                                                                                                    \
+        if (smem > 48 * 1024) CK(ctx, cudaFuncSetAttribute(mg::phasor_scan_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        mg::phasor_scan_kernel<K><<<blocks, 64, smem, ctx->stream>>>(a.bits, a.nbits, a.F, a.nsym, a.sps, a.sample0, p, d_state, aligned4); \
+    } while (0)
+        if (ph.kind == MODEM_PHASOR_BFSK) MG_SCAN(mg::kPhBfsk);
+        else if (ph.kind == MODEM_PHASOR_MFSK) MG_SCAN(mg::kPhMfsk);
+        else MG_SCAN(mg::kPhDmpsk);
+#undef MG_SCAN
         ctx->launches++;
         CK(ctx, cudaGetLastError());
+        if (ph.kind == MODEM_PHASOR_DMPSK) {
+            rc = ensure(ctx, ctx->s_siq, a.F * a.nsym * sizeof(float2));
+            if (rc) return rc;
+            const u64 n = a.F * a.nsym;
+            const unsigned sb = (unsigned)std::min<u64>((n + mg::kThreads - 1) / mg::kThreads, (u64)ctx->sm_count * 32);
+            mg::phasor_symbol_iq_kernel<<<sb, mg::kThreads, 0, ctx->stream>>>(p.state, n, p.amplitude, (float2*)ctx->s_siq.p);
+            ctx->launches++;
+            CK(ctx, cudaGetLastError());
+            p.siq = (const float2*)ctx->s_siq.p;
+        }
     }
-    const u64 tile = (u64)mg::kThreads * 4;
+    if (ph.kind == MODEM_PHASOR_CPFSK) {
+        /* per-(symbol value, sample) table, shared by every frame: worth it once the frames outnumber the rows */
+        const u64 n_sym = 1ull << ph.bits_per_symbol;
+        const size_t bytes = n_sym * a.L * sizeof(float2);
+        if (a.F >= 2 * n_sym && bytes <= ((size_t)256 << 20) && !ctx->n_channels) {
+            modem_ctx::CpKey key{a.L, a.sample0, ph.deviation, ph.amplitude, ph.bits_per_symbol};
+            if (!(key == ctx->cp_key)) {
+                int rc = ensure(ctx, ctx->s_cptab, bytes);
+                if (rc) return rc;
+                const unsigned tb = (unsigned)std::min<u64>((n_sym * a.L + mg::kThreads - 1) / mg::kThreads, (u64)ctx->sm_count * 32);
+                mg::cpfsk_table_kernel<<<tb, mg::kThreads, 0, ctx->stream>>>((float2*)ctx->s_cptab.p, a.L, (uint32_t)n_sym, p, a.sample0);
+                ctx->launches++;
+                CK(ctx, cudaGetLastError());
+                ctx->cp_key = key;
+            }
+            p.cp_tab = (const float2*)ctx->s_cptab.p;
+        }
+    }
+    const bool vec = (a.L % 2 == 0) && aligned16(a.tx) && aligned16(a.iq);
+    const u64 tile = (u64)mg::kThreads * 2 * (vec ? 2 : 1);
     const u64 tiles = (a.L + tile - 1) / tile;
     a.frames_per_block = frames_per_block(ctx, a.F, tiles);
     dim3 grid((unsigned)tiles, (unsigned)((a.F + a.frames_per_block - 1) / a.frames_per_block));
+#define MG_PH_LAUNCH(K)                                                                                   \
+    do {                                                                                                  \
+        if (vec) mg::tx_phasor_kernel<K, 2><<<grid, mg::kThreads, 0, ctx->stream>>>(a, p);                \
+        else mg::tx_phasor_kernel<K, 1><<<grid, mg::kThreads, 0, ctx->stream>>>(a, p);                    \
+    } while (0)
     switch (ph.kind) {
-    case MODEM_PHASOR_BFSK: mg::tx_phasor_kernel<mg::kPhBfsk><<<grid, mg::kThreads, 0, ctx->stream>>>(a, p); break;
-    case MODEM_PHASOR_MFSK: mg::tx_phasor_kernel<mg::kPhMfsk><<<grid, mg::kThreads, 0, ctx->stream>>>(a, p); break;
-    case MODEM_PHASOR_CPFSK: mg::tx_phasor_kernel<mg::kPhCpfsk><<<grid, mg::kThreads, 0, ctx->stream>>>(a, p); break;
-    case MODEM_PHASOR_MSK: mg::tx_phasor_kernel<mg::kPhMsk><<<grid, mg::kThreads, 0, ctx->stream>>>(a, p); break;
-    case MODEM_PHASOR_DMPSK: mg::tx_phasor_kernel<mg::kPhDmpsk><<<grid, mg::kThreads, 0, ctx->stream>>>(a, p); break;
+    case MODEM_PHASOR_BFSK: MG_PH_LAUNCH(mg::kPhBfsk); break;
+    case MODEM_PHASOR_MFSK: MG_PH_LAUNCH(mg::kPhMfsk); break;
+    case MODEM_PHASOR_CPFSK: MG_PH_LAUNCH(mg::kPhCpfsk); break;
+    case MODEM_PHASOR_MSK: MG_PH_LAUNCH(mg::kPhMsk); break;
+    case MODEM_PHASOR_DMPSK: MG_PH_LAUNCH(mg::kPhDmpsk); break;
     default: return fail(ctx, MODEM_ERR_INVALID, "unknown phasor kind");
     }
+#undef MG_PH_LAUNCH
     ctx->launches++;
     CK(ctx, cudaGetLastError());
     return MODEM_OK;
@@ -681,7 +737,7 @@ void modem_gpu_destroy(modem_ctx_t* ctx)
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     void* ptrs[] = {ctx->d_lut, ctx->d_slut, ctx->d_tx_taps, ctx->d_rx_taps, ctx->d_chan_w, ctx->d_chan_po, ctx->d_counters,
                     ctx->s_bits.p, ctx->s_tx.p, ctx->s_iq.p, ctx->s_rx.p, ctx->s_sym.p, ctx->s_bits_out.p, ctx->s_soft.p, ctx->s_filt.p,
-                    ctx->s_state.p, ctx->s_re.p, ctx->s_raw.p, ctx->s_po.p, ctx->s_hilbert.p};
+                    ctx->s_state.p, ctx->s_re.p, ctx->s_raw.p, ctx->s_po.p, ctx->s_hilbert.p, ctx->s_siq.p, ctx->s_cptab.p};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     for (auto& ln : ctx->lanes) {

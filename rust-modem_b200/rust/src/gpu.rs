@@ -42,6 +42,24 @@ pub struct modem_cfg_t {
     pub flags: u32,
 }
 
+/// Stateful / time-varying mappers (digital/{bfsk,mfsk,cpfsk,msk,dmpsk}.rs): `modem_phasor_t`.
+#[repr(C)]
+#[derive(Copy, Clone, Debug, Default)]
+pub struct modem_phasor_t {
+    pub struct_size: u32,
+    pub kind: u32, // MODEM_PHASOR_*: 1 bfsk, 2 mfsk, 3 cpfsk, 4 msk, 5 dmpsk
+    pub bits_per_symbol: u32,
+    pub amplitude: f32,
+    pub deviation: f32,
+    pub phase: f32,
+    pub shift: f32,
+    pub mfsk_increase_map: u32,
+}
+pub const MODEM_SAMPLES_C32: u32 = 0;
+pub const MODEM_SAMPLES_F32: u32 = 1;
+pub const MODEM_SAMPLES_I16: u32 = 2;
+pub const LOCK_SAMPLES: usize = 64; // demodulator.rs:5
+
 pub enum modem_ctx_t {}
 
 extern "C" {
@@ -66,6 +84,20 @@ extern "C" {
     pub fn modem_gpu_loopback(ctx: *mut modem_ctx_t, bits: *const u8, f: usize, nbits: usize, sigma: f32, seed: u64,
                               frame0: u64, tx: *mut modem_c32_t, sym: *mut u8, bits_out: *mut u8,
                               counters: *mut u64) -> c_int;
+    pub fn modem_hilbert_taps(n: *mut usize) -> *const f32;
+    pub fn modem_phasor_by_name(name: *const c_char, baud_rate: usize, sample_rate: usize, out: *mut modem_phasor_t,
+                                evenodd: *mut u32) -> c_int;
+    pub fn modem_gpu_set_phasor(ctx: *mut modem_ctx_t, phasor: *const modem_phasor_t) -> c_int;
+    pub fn modem_gpu_preamble(ctx: *mut modem_ctx_t, f: usize, n: usize, amplitude: f32, tx: *mut modem_c32_t) -> c_int;
+    pub fn modem_gpu_modulate_real(ctx: *mut modem_ctx_t, bits: *const u8, f: usize, nbits: usize, preamble: usize,
+                                   preamble_amplitude: f32, out: *mut f32) -> c_int;
+    pub fn modem_gpu_lock_phase(ctx: *mut modem_ctx_t, samples: *const c_void, fmt: u32, f: usize, l: usize,
+                                hilbert_taps: *const f32, n_hilbert: usize, lock_samples: usize,
+                                phase_offset: *mut f32) -> c_int;
+    pub fn modem_gpu_demodulate_real(ctx: *mut modem_ctx_t, samples: *const c_void, fmt: u32, f: usize, l: usize,
+                                     lock_samples: usize, hilbert_taps: *const f32, n_hilbert: usize,
+                                     phase_offset: *mut f32, sym: *mut u8, bits: *mut u8, soft: *mut modem_c32_t,
+                                     filt: *mut modem_c32_t) -> c_int;
     pub fn modem_gpu_strerror(code: c_int) -> *const c_char;
     pub fn modem_gpu_last_error(ctx: *const modem_ctx_t) -> *const c_char;
 }
@@ -145,6 +177,52 @@ impl Context {
                                             std::ptr::null_mut(), filt.as_mut_ptr(), 0.0, 0, 0) },
               self.raw, "modem_gpu_demodulate");
         filt
+    }
+
+    /// Switch the TX mapper to one of the stateful schemes (`bfsk`, `mfsk`, `16cpfsk`, `msk`, `dqpsk`, `dbpsk`:
+    /// modulate.rs:74-95); the `DigitalPhasor::update` recurrence then runs in the phasor kernels.
+    pub fn set_phasor(&mut self, p: &modem_phasor_t) {
+        check(unsafe { modem_gpu_set_phasor(self.raw, p) }, self.raw, "modem_gpu_set_phasor");
+    }
+
+    /// `Modulator::new(&mut carrier, Box::new(phasor::Raw::new(amplitude))).take(n)` mapped through
+    /// `modulate()` (modulate.rs:118-126).
+    pub fn preamble(&mut self, n: usize, amplitude: f32) -> Vec<modem_c32_t> {
+        let mut tx = vec![modem_c32_t::default(); n];
+        check(unsafe { modem_gpu_preamble(self.raw, 1, n, amplitude, tx.as_mut_ptr()) }, self.raw, "modem_gpu_preamble");
+        tx
+    }
+
+    /// Everything src/bin/modulate.rs writes without `--iq` for one stream: sync tone, then data, real part.
+    pub fn modulate_real(&mut self, bits: &[u8], preamble: usize, amplitude: f32) -> Vec<f32> {
+        let l = unsafe { modem_gpu_frame_samples(self.raw, bits.len()) };
+        let mut out = vec![0f32; preamble + l];
+        check(unsafe { modem_gpu_modulate_real(self.raw, bits.as_ptr(), 1, bits.len(), preamble, amplitude, out.as_mut_ptr()) },
+              self.raw, "modem_gpu_modulate_real");
+        out
+    }
+
+    /// `Demodulator::lock_phase` (demodulator.rs:32-36) on an analytic signal: returns `pll.phase_offset`.
+    pub fn lock_phase(&mut self, sig: &[modem_c32_t]) -> f32 {
+        let mut po = 0f32;
+        check(unsafe { modem_gpu_lock_phase(self.raw, sig.as_ptr() as *const c_void, MODEM_SAMPLES_C32, 1, sig.len(),
+                                            std::ptr::null(), 0, LOCK_SAMPLES, &mut po) },
+              self.raw, "modem_gpu_lock_phase");
+        po
+    }
+
+    /// src/bin/demodulate.rs:29-43 for one stream of native-endian i16 samples: Hilbert FIR + 64-sample PLL lock +
+    /// the two low-pass FIRs; returns (locked phase offset, the `(i, q)` stream the binary prints).
+    pub fn demodulate_i16(&mut self, samples: &[i16]) -> (f32, Vec<modem_c32_t>) {
+        assert!(samples.len() >= LOCK_SAMPLES, "called `Option::unwrap()` on a `None` value"); // demodulator.rs:34
+        let mut po = 0f32;
+        let mut filt = vec![modem_c32_t::default(); samples.len() - LOCK_SAMPLES];
+        check(unsafe { modem_gpu_demodulate_real(self.raw, samples.as_ptr() as *const c_void, MODEM_SAMPLES_I16, 1,
+                                                 samples.len(), LOCK_SAMPLES, std::ptr::null(), 0, &mut po,
+                                                 std::ptr::null_mut(), std::ptr::null_mut(), std::ptr::null_mut(),
+                                                 filt.as_mut_ptr()) },
+              self.raw, "modem_gpu_demodulate_real");
+        (po, filt)
     }
 
     /// Batched loopback over `frames` frames of `nbits` bits each: returns (bit errors, bits compared).
