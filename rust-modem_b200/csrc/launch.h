@@ -20,6 +20,11 @@ bool rx_fast_supported(uint32_t n_taps);
 uint64_t rx_fast_tiles(uint32_t n_taps, uint64_t K, int variant);
 cudaError_t rx_fast_launch(const RxArgs& a, const float* h_taps, bool fma, int variant, cudaStream_t stream);
 
+/* rx_fullrate_fast.cu: the full-rate (I,Q) stream, 64 taps; needs L even and a 16-byte aligned filt row base */
+bool rx_fullrate_fast_supported(uint32_t n_taps);
+uint64_t rx_fullrate_fast_tiles(uint64_t L);
+cudaError_t rx_fullrate_fast_launch(const RxArgs& a, const float* h_taps, bool fma, bool per_frame_po, cudaStream_t stream);
+
 /* tx_fast.cu */
 bool tx_rect_fast_supported(uint32_t bps);
 uint64_t tx_rect_fast_tiles(uint64_t L);

@@ -414,7 +414,18 @@ int launch_rx(modem_ctx* ctx, const float2* d_rx, u64 F, u64 L, uint8_t* d_sym, 
     const bool fma = (c.flags & MODEM_FLAG_FUSED_MAC) != 0;
     const uint32_t N = c.n_rx_taps, sps = c.samples_per_symbol;
 
-    if (d_filt) {
+    if (d_filt && !ctx->force_generic && mg::rx_fullrate_fast_supported(N) && (L % 2 == 0) && aligned16(d_filt) && a.nz.sigma == 0.0f) {
+        /* the tuned full-rate kernel: sliding register window, packed MACs (rx_fullrate_fast.cu) */
+        const bool pfp = a.ch.po_frame != nullptr;
+        a.frames_per_block = std::min<uint32_t>(frames_per_block(ctx, F, mg::rx_fullrate_fast_tiles(L)), 8);
+        if (ctx->n_channels) while (ctx->frames_per_channel % a.frames_per_block || ctx->frame_base % a.frames_per_block) --a.frames_per_block;
+        if (!pfp && !src) { /* per-call phase offset: NCO from the context's table (one slice per channel) */
+            int rc = attach_carrier_table(ctx, a.ch, F, L, true);
+            if (rc) return rc;
+        }
+        CK(ctx, mg::rx_fullrate_fast_launch(a, ctx->h_rx_taps.data(), fma, pfp, ctx->stream));
+        ctx->launches++;
+    } else if (d_filt) {
         const uint32_t TILE = mg::kThreads * 4;
         const size_t smem = (size_t)(TILE + N - 1) * 8 + (size_t)N * 4;
         if (smem > 200 * 1024) return fail(ctx, MODEM_ERR_UNSUPPORTED, "rx_taps too long for shared memory");

@@ -91,8 +91,35 @@ def demodulate_real(wire_f32, fmt):
     m.close()
 
 
+def fullrate(fmt, Fx=1024):
+    """What iterating the reference's Demodulator yields: the filtered (I,Q) for EVERY input sample (demodulator.rs:44-55),
+    2 x 64 MACs per sample -- FP32-lane bound by construction (256 lane-ops per sample: <= 145 GS/s exact)."""
+    lp = pkg.lowpass_taps()
+    m = pkg.Modem(scheme="qpsk", baud_rate=1250, sample_rate=10000, carrier_hz=2500, rx_taps=lp, decision_delay=35,
+                  slicer_gain=float(np.float32(lp.sum())))
+    st = torch.cuda.current_stream()
+    m.set_stream(st.cuda_stream)
+    n = Fx * LSAMP
+    if fmt == "c32":
+        x = torch.randn((Fx, LSAMP, 2), dtype=torch.float32, device="cuda")
+        filt = torch.empty((Fx, LSAMP, 2), dtype=torch.float32, device="cuda")
+        ms = timeit(lambda: m.demodulate_into(x, Fx, LSAMP, filt=filt), st)
+        b = 16
+    else:
+        x = (torch.randn((Fx, LSAMP + 64), dtype=torch.float32, device="cuda") * 3000).to(torch.int16)
+        filt = torch.empty((Fx, LSAMP, 2), dtype=torch.float32, device="cuda")
+        po = torch.empty(Fx, dtype=torch.float32, device="cuda")
+        ms = timeit(lambda: m._ck(L_.modem_gpu_demodulate_real(m._ctx, x.data_ptr(), pkg.capi.SAMPLES_I16, Fx, LSAMP + 64, 64, None, 0,
+                                                               po.data_ptr(), None, None, None, filt.data_ptr())), st)
+        b = 10
+    print(json.dumps({"row": f"Demodulator iterator, full-rate (I,Q) out, {fmt} in ({Fx} frames)", "ms": round(ms, 4),
+                      "Msamples_s": round(n / ms / 1e3), "bytes_per_sample": b, "GBs": round(n * b / ms / 1e6),
+                      "frac_hbm": round(n * b / ms / 1e6 / PEAK, 3), "frac_fp32_lane_bound": round(n / ms / 1e3 / 145000, 3)}), flush=True)
+    m.close()
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["stateful", "real"]
+    which = sys.argv[1:] or ["stateful", "real", "fullrate"]
     if "stateful" in which:
         for s in ("16cpfsk", "msk", "bfsk", "mfsk", "dqpsk"):
             stateful(s)
@@ -101,3 +128,6 @@ if __name__ == "__main__":
         demodulate_real(w, "i16")
         demodulate_real(w, "f32")
         demodulate_real(w, "f32-nolock")
+    if "fullrate" in which:
+        fullrate("c32")
+        fullrate("i16")
