@@ -70,8 +70,8 @@ struct modem_ctx {
     /* NCO tables (ChannelView::cs_tab): TX view (no phase offset) and RX view (with it); cached by key */
     Scratch s_cs_tx, s_cs_rx;
     struct CsKey {
-        u64 len = 0, ch0 = 0, nch = 0, ver = ~0ull;
-        bool operator==(const CsKey& o) const { return len == o.len && ch0 == o.ch0 && nch == o.nch && ver == o.ver; }
+        u64 len = 0, ch0 = 0, nch = 0, ver = ~0ull, s0 = 0;
+        bool operator==(const CsKey& o) const { return len == o.len && ch0 == o.ch0 && nch == o.nch && ver == o.ver && s0 == o.s0; }
     } cs_key;
     bool cs_rx_shared = true; /* every phase offset is 0: the RX view is the TX table */
     u64 chan_version = 0;
@@ -230,16 +230,18 @@ bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) ==
  */
 constexpr u64 kCsPadLo = 160, kCsPadHi = 4352; /* zero margins so RX tiles can read past both frame ends unguarded */
 
-int attach_carrier_table(modem_ctx* ctx, mg::ChannelView& view, u64 F, u64 len, bool rx)
+int attach_carrier_table(modem_ctx* ctx, mg::ChannelView& view, u64 F, u64 len, bool rx, u64 sample_skip = 0)
 {
+    const u64 s0 = ctx->cfg.sample0 + sample_skip; /* Carrier.sample of the frames' first sample */
     const u64 fpc = ctx->n_channels ? ctx->frames_per_channel : 1;
     const u64 ch0 = ctx->n_channels ? ctx->frame_base / fpc : 0;
     const u64 ch1 = ctx->n_channels ? (ctx->frame_base + F - 1) / fpc : 0;
     modem_ctx::CsKey key;
     key.len = len;
     key.ver = ctx->chan_version;
+    key.s0 = s0;
     /* keep a wider cached range if it already covers this call */
-    if (ctx->cs_key.len == len && ctx->cs_key.ver == key.ver && ctx->cs_key.ch0 <= ch0 &&
+    if (ctx->cs_key.len == len && ctx->cs_key.ver == key.ver && ctx->cs_key.s0 == s0 && ctx->cs_key.ch0 <= ch0 &&
         ch1 < ctx->cs_key.ch0 + ctx->cs_key.nch) {
         key = ctx->cs_key;
     } else {
@@ -252,12 +254,12 @@ int attach_carrier_table(modem_ctx* ctx, mg::ChannelView& view, u64 F, u64 len, 
         if (rc) return rc;
         mg::ChannelView cv = channel_view(ctx);
         const unsigned blocks = (unsigned)std::min<u64>((key.nch * row + mg::kThreads - 1) / mg::kThreads, (u64)ctx->sm_count * 16);
-        mg::carrier_table_kernel<<<blocks, mg::kThreads, 0, ctx->stream>>>((float2*)ctx->s_cs_tx.p, len, kCsPadLo, kCsPadHi, key.ch0, key.nch, cv, ctx->cfg.sample0, 0);
+        mg::carrier_table_kernel<<<blocks, mg::kThreads, 0, ctx->stream>>>((float2*)ctx->s_cs_tx.p, len, kCsPadLo, kCsPadHi, key.ch0, key.nch, cv, s0, 0);
         ctx->launches++;
         if (!ctx->cs_rx_shared) {
             rc = ensure(ctx, ctx->s_cs_rx, bytes);
             if (rc) return rc;
-            mg::carrier_table_kernel<<<blocks, mg::kThreads, 0, ctx->stream>>>((float2*)ctx->s_cs_rx.p, len, kCsPadLo, kCsPadHi, key.ch0, key.nch, cv, ctx->cfg.sample0, 1);
+            mg::carrier_table_kernel<<<blocks, mg::kThreads, 0, ctx->stream>>>((float2*)ctx->s_cs_rx.p, len, kCsPadLo, kCsPadHi, key.ch0, key.nch, cv, s0, 1);
             ctx->launches++;
         }
         CK(ctx, cudaGetLastError());
@@ -316,11 +318,12 @@ int launch_tx(modem_ctx* ctx, const uint8_t* d_bits, u64 F, u64 nbits, float2* d
         const uint32_t bps = c.bits_per_symbol;
         const bool word_ok = mg::tx_rect_fast_supported(bps) && (nbits % bps == 0) &&
                              ((reinterpret_cast<uintptr_t>(d_bits) % bps) == 0);
-        const bool fast = plain && !ctx->force_generic && vec_ok && d_tx && !d_iq && c.q_offset == 0 && c.n_tables == 1 &&
-                          (c.samples_per_symbol % 2 == 0) && word_ok && a.L < (1ull << 32);
+        const bool fast_shape = !ctx->force_generic && !d_iq && c.q_offset == 0 && c.n_tables == 1 && (c.samples_per_symbol % 2 == 0) &&
+                                word_ok && a.L < (1ull << 32) && (a.L % 2 == 0);
+        const bool fast = fast_shape && ((plain && vec_ok && d_tx) || (ro && ro->re && !d_tx));
         if (fast) {
             a.frames_per_block = frames_per_block(ctx, F, mg::tx_rect_fast_tiles(a.L));
-            int rc = attach_carrier_table(ctx, a.ch, F, a.L, false);
+            int rc = attach_carrier_table(ctx, a.ch, F, a.L, false, ro ? ro->sample_skip : 0);
             if (rc) return rc;
             CK(ctx, mg::tx_rect_fast_launch(a, ctx->stream));
         } else {

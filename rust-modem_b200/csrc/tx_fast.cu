@@ -14,7 +14,7 @@ namespace mg {
  * with all bit loads of the batch issued first, so FU*U independent loads are in flight
  * per thread instead of one dependent chain per frame.
  */
-template <int BPS>
+template <int BPS, bool REAL>
 __global__ void __launch_bounds__(kThreads, 4) tx_rect_fast_kernel(const __grid_constant__ TxArgs a)
 {
     constexpr int U = 2, FU = 4;
@@ -48,8 +48,20 @@ __global__ void __launch_bounds__(kThreads, 4) tx_rect_fast_kernel(const __grid_
     }
 
     const uint8_t* pb = a.bits + f0 * a.nbits;
-    float4* po = reinterpret_cast<float4*>(a.tx + f0 * a.L);
+    float4* po = REAL ? nullptr : reinterpret_cast<float4*>(a.tx + f0 * a.L);
     const u64 Lq = a.L / 2; /* float4 per frame row */
+    /* REAL: the wire format of src/bin/modulate.rs:128-133 -- `x.modulate().re` only, 4 bytes per sample; rows may
+     * start at an odd float (odd preamble length), so the pair is written as two 32-bit stores */
+    float* pr = REAL ? a.re + f0 * a.re_stride + a.re_offset : nullptr;
+    auto emit = [&](int j, int u, float2 o0, float2 o1) {
+        if (REAL) {
+            float* q = pr + (u64)j * a.re_stride + 2 * (u64)noff[u];
+            __stcs(q, o0.x);
+            __stcs(q + 1, o1.x);
+        } else {
+            __stcs(po + j * Lq + noff[u], make_float4(o0.x, o0.y, o1.x, o1.y));
+        }
+    };
     u64 f = f0;
     for (; f + FU <= f1; f += FU) {
         uint32_t idx[FU][U];
@@ -64,10 +76,11 @@ __global__ void __launch_bounds__(kThreads, 4) tx_rect_fast_kernel(const __grid_
                 const float2 bb = s_lut[idx[j][u]];
                 const float2 o0 = mix_iq(bb.x, bb.y, c0[u], s0[u]);
                 const float2 o1 = mix_iq(bb.x, bb.y, c1[u], s1[u]);
-                if (valid[u]) __stcs(po + j * Lq + noff[u], make_float4(o0.x, o0.y, o1.x, o1.y));
+                if (valid[u]) emit(j, u, o0, o1);
             }
         pb += FU * a.nbits;
-        po += FU * Lq;
+        if (REAL) pr += FU * a.re_stride;
+        else po += FU * Lq;
     }
     for (; f < f1; ++f) {
 #pragma unroll
@@ -76,10 +89,11 @@ __global__ void __launch_bounds__(kThreads, 4) tx_rect_fast_kernel(const __grid_
             const float2 bb = s_lut[load_symbol_word<BPS>(pb + koff[u])];
             const float2 o0 = mix_iq(bb.x, bb.y, c0[u], s0[u]);
             const float2 o1 = mix_iq(bb.x, bb.y, c1[u], s1[u]);
-            __stcs(po + noff[u], make_float4(o0.x, o0.y, o1.x, o1.y));
+            emit(0, u, o0, o1);
         }
         pb += a.nbits;
-        po += Lq;
+        if (REAL) pr += a.re_stride;
+        else po += Lq;
     }
 }
 
@@ -207,11 +221,20 @@ uint64_t tx_rect_fast_tiles(uint64_t L) { return (L + 4 * kThreads - 1) / (4 * k
 cudaError_t tx_rect_fast_launch(const TxArgs& a, cudaStream_t stream)
 {
     dim3 grid((unsigned)tx_rect_fast_tiles(a.L), (unsigned)((a.F + a.frames_per_block - 1) / a.frames_per_block));
+    if (a.re && !a.tx) {
+        switch (a.bps) {
+        case 1: tx_rect_fast_kernel<1, true><<<grid, kThreads, 0, stream>>>(a); break;
+        case 2: tx_rect_fast_kernel<2, true><<<grid, kThreads, 0, stream>>>(a); break;
+        case 4: tx_rect_fast_kernel<4, true><<<grid, kThreads, 0, stream>>>(a); break;
+        default: tx_rect_fast_kernel<8, true><<<grid, kThreads, 0, stream>>>(a); break;
+        }
+        return cudaGetLastError();
+    }
     switch (a.bps) {
-    case 1: tx_rect_fast_kernel<1><<<grid, kThreads, 0, stream>>>(a); break;
-    case 2: tx_rect_fast_kernel<2><<<grid, kThreads, 0, stream>>>(a); break;
-    case 4: tx_rect_fast_kernel<4><<<grid, kThreads, 0, stream>>>(a); break;
-    default: tx_rect_fast_kernel<8><<<grid, kThreads, 0, stream>>>(a); break;
+    case 1: tx_rect_fast_kernel<1, false><<<grid, kThreads, 0, stream>>>(a); break;
+    case 2: tx_rect_fast_kernel<2, false><<<grid, kThreads, 0, stream>>>(a); break;
+    case 4: tx_rect_fast_kernel<4, false><<<grid, kThreads, 0, stream>>>(a); break;
+    default: tx_rect_fast_kernel<8, false><<<grid, kThreads, 0, stream>>>(a); break;
     }
     return cudaGetLastError();
 }

@@ -69,6 +69,20 @@ def test_modulate_real(pkg, orc, scheme, preamble):
     assert_buffers(got, ref, f"{scheme} real output, preamble {preamble}")
 
 
+@pytest.mark.parametrize("scheme", ["qpsk", "qam16", "bpsk", "qam256"])
+@pytest.mark.parametrize("preamble", [0, 29, 64])
+def test_modulate_real_fast_kernel(pkg, orc, scheme, preamble):
+    """sps 8 takes the tuned TX kernel's real-output mode (two 32-bit stores per thread, NCO table built for
+    Carrier.sample = preamble); odd preambles make every row start on an odd float."""
+    kw = dict(scheme=scheme, baud_rate=1250, sample_rate=10000, carrier_hz=2500)
+    m, o = pkg.Modem(**kw), orc.OraclePath(**kw)
+    bits = rand_bits(33, 37, 1300 * o.bps)
+    assert_buffers(m.modulate_real(bits, preamble=preamble), o.modulate_real(bits, preamble=preamble),
+                   f"{scheme} real output (fast kernel), preamble {preamble}")
+    # and the complex entry afterwards still uses its own table (sample0 = 0)
+    assert_buffers(m.modulate(bits), o.modulate(bits), f"{scheme} complex output after a real call")
+
+
 def test_modulate_real_shaped(pkg, orc):
     rrc = orc.rrc_taps(16, 8, 0.35)
     kw = dict(scheme="qpsk", baud_rate=1250, sample_rate=10000, carrier_hz=2500, tx_taps=rrc, rx_taps=rrc,
