@@ -293,8 +293,9 @@ def main():
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "frames_per_gpu": F, "samples_per_frame": L,
                        "l2": "per step 2 GiB of TX samples are written and read per GPU (16x the 126 MB L2), no flush "
-                             "between steps; the library pipelines TX/RX in ~48 MB chunks so RX reads come from L2; "
-                             "roofline.kernels are timed separately as whole-buffer serial launches",
+                             "between steps: every step's inputs are far larger than L2; a step is one whole-buffer TX launch and one "
+                             "whole-buffer RX launch (the library's chunked TX||RX pipeline is off by default, DESIGN.md 4); "
+                             "roofline.kernels are the same two launches timed separately",
                        "parallelism": f"frames sharded over {world} GPU(s), one NCCL all-reduce of 2 u64 counters"},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": ach[dom], "peak": peak, "unit": "GB/s",
@@ -308,7 +309,7 @@ def main():
         }
         if world == 1 and not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
-            frames = 32 * threads
+            frames = 64 * threads
             v, dt = cpu_baseline(frames, threads)
             v1, _ = cpu_baseline(8, 1)
             out["cpu_baseline"] = {"value": v, "unit": "Msamples/s", "cores": threads, "kind": "port",

@@ -213,9 +213,14 @@ __global__ void __launch_bounds__(kThreads) awgn_kernel(float2* buf, u64 F, u64 
 
 /*
  * Generic decimating RX (any sps / tap count / q_offset): one thread per symbol.
- * dynamic smem: float2 s_cs[R]; float s_vi[R]; float s_vq[R]; float s_taps[N]
- *   with R = (TS-1)*sps + N + q_offset samples per tile.
+ * dynamic smem: float2 s_cs[R]; float s_vi[RP]; float s_vq[RP]; float s_taps[N]
+ *   with R = (TS-1)*sps + N + q_offset samples per tile and RP = R + R/32 + 1: element j of a rail lives at
+ *   j + j/32.  The threads of a warp read elements sps apart; for sps = 4, 8, 16 the unskewed layout puts them on
+ *   32/sps banks (8-way conflicts at sps 8 -- measured 4.5 ms where the skewed layout needs 2); the one-word skew
+ *   per 32 elements spreads any power-of-two stride over all banks and costs nothing for odd sps.
  */
+__host__ __device__ __forceinline__ uint32_t rx_generic_skew(uint32_t j) { return j + (j >> 5); }
+
 template <bool FMA>
 __global__ void __launch_bounds__(kThreads) rx_generic_kernel(const __grid_constant__ RxArgs a)
 {
@@ -223,39 +228,48 @@ __global__ void __launch_bounds__(kThreads) rx_generic_kernel(const __grid_const
     __shared__ float2 s_slut[kMaxLut];
     const uint32_t TS = a.sym_tile, sps = a.sps, N = a.n_taps;
     const uint32_t R = (TS - 1) * sps + N + a.q_offset;
+    const uint32_t RP = rx_generic_skew(R) + 1;
     float2* s_cs = reinterpret_cast<float2*>(smem_raw);
     float* s_vi = reinterpret_cast<float*>(s_cs + R);
-    float* s_vq = s_vi + R;
-    float* s_taps = s_vq + R;
+    float* s_vq = s_vi + RP;
+    float* s_taps = s_vq + RP;
 
     for (uint32_t i = threadIdx.x; i < a.n_tables * a.n_const; i += kThreads) s_slut[i] = a.slut[i];
     for (uint32_t i = threadIdx.x; i < N; i += kThreads) s_taps[i] = a.taps[i];
 
     const u64 f0 = (u64)blockIdx.y * a.frames_per_block;
     const u64 f1 = min(a.F, f0 + a.frames_per_block);
-    const float w = chan_w(a.ch, f0), po = chan_po(a.ch, f0);
+    const float w = chan_w(a.ch, f0);
+    const bool pfp = a.ch.po_frame != nullptr; /* every frame has its own PLL offset */
+    const float po = pfp ? 0.0f : chan_po(a.ch, f0);
     const u64 k0 = (u64)blockIdx.x * TS;
     /* sample index of s_v*[0]; may be negative (zero history, fir.rs:13) */
     const long long nb = (long long)(k0 * sps + a.delay) - (long long)(N - 1);
     for (uint32_t j = threadIdx.x; j < R; j += kThreads) {
         long long n = nb + j;
         float s = 0.0f, c = 0.0f;
-        if (n >= 0 && (u64)n < a.L) mg_sincosf(__fadd_rn(nco_phase(w, a.sample0 + (u64)n), po), &s, &c);
+        if (n >= 0 && (u64)n < a.L) {
+            const float ph = nco_phase(w, a.sample0 + (u64)n);
+            if (pfp) c = ph; /* the frame-invariant part; the offset is added per frame below */
+            else mg_sincosf(__fadd_rn(ph, po), &s, &c);
+        }
         s_cs[j] = make_float2(c, s);
     }
 
     uint32_t err = 0, cmp = 0;
     for (u64 f = f0; f < f1; ++f) {
+        const float pof = pfp ? chan_po(a.ch, f) : 0.0f;
         __syncthreads();
         for (uint32_t j = threadIdx.x; j < R; j += kThreads) {
             long long n = nb + j;
             float2 v = make_float2(0.0f, 0.0f);
             if (n >= 0 && (u64)n < a.L) {
                 float2 cs = s_cs[j];
+                if (pfp) mg_sincosf(__fadd_rn(cs.x, pof), &cs.y, &cs.x);
                 v = rx_mix(a, f, a.nz.frame0 + f, (u64)n, cs.x, cs.y);
             }
-            s_vi[j] = v.x;
-            s_vq[j] = v.y;
+            s_vi[rx_generic_skew(j)] = v.x;
+            s_vq[rx_generic_skew(j)] = v.y;
         }
         __syncthreads();
         for (uint32_t t = threadIdx.x; t < TS; t += kThreads) {
@@ -266,8 +280,8 @@ __global__ void __launch_bounds__(kThreads) rx_generic_kernel(const __grid_const
             float ai = 0.0f, aq = 0.0f;
             for (uint32_t i = 0; i < N; ++i) {
                 float c = s_taps[i];
-                ai = mac<FMA>(ai, s_vi[ji - i], c);
-                aq = mac<FMA>(aq, s_vq[jq - i], c);
+                ai = mac<FMA>(ai, s_vi[rx_generic_skew(ji - i)], c);
+                aq = mac<FMA>(aq, s_vq[rx_generic_skew(jq - i)], c);
             }
             const float I = __fmul_rn(a.rx_gain, ai), Q = __fmul_rn(a.rx_gain, aq);
             const uint32_t s = slice_point(s_slut + (k % a.n_tables) * a.n_const, a.n_const, I, Q);

@@ -460,20 +460,19 @@ int launch_rx(modem_ctx* ctx, const float2* d_rx, u64 F, u64 L, uint8_t* d_sym, 
         CK(ctx, mg::rx_fast_launch(a, ctx->h_rx_taps.data(), fma, ctx->rx_variant, ctx->stream));
     } else {
         const size_t budget = 96 * 1024;
-        if ((size_t)N * 4 + (size_t)(N + c.q_offset) * 16 > budget)
+        if ((size_t)N * 4 + (size_t)(N + c.q_offset) * 17 + 64 > budget)
             return fail(ctx, MODEM_ERR_UNSUPPORTED, "rx_taps too long for shared memory");
-        const size_t rmax = (budget - (size_t)N * 4) / 16;
+        const size_t rmax = (budget - (size_t)N * 4 - 64) / 17; /* 8 B of NCO + 2 skewed rails (4 + 1/8 B each) per staged sample */
         uint32_t TS = (uint32_t)std::min<size_t>(256, (rmax - N - c.q_offset) / sps + 1);
         TS = std::max<uint32_t>(TS, 1);
         a.sym_tile = TS;
         const size_t R = (size_t)(TS - 1) * sps + N + c.q_offset;
-        const size_t smem = R * 16 + (size_t)N * 4;
+        const size_t RP = mg::rx_generic_skew((uint32_t)R) + 1;
+        const size_t smem = R * 8 + 2 * RP * 4 + (size_t)N * 4;
         const u64 tiles = (a.K + TS - 1) / TS;
         a.frames_per_block = frames_per_block(ctx, F, tiles);
-        if (src && src->d_po) { /* every frame has its own phase offset: the CTA's NCO values serve one frame */
-            if (F > 65535) return fail(ctx, MODEM_ERR_UNSUPPORTED, "per-frame phase offsets limited to 65535 frames per call");
-            a.frames_per_block = 1;
-        }
+        /* per-frame phase offsets (PLL lock): the CTA keeps the frame-invariant NCO phase of its tile and adds
+         * each frame's offset before the sincos, so it still loops over several frames */
         dim3 grid((unsigned)tiles, (unsigned)((F + a.frames_per_block - 1) / a.frames_per_block));
         if (fma) {
             CK(ctx, cudaFuncSetAttribute(mg::rx_generic_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
