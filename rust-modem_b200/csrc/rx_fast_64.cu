@@ -25,6 +25,8 @@ cudaError_t rx_fast_launch_64(const RxArgs& a, const float* h_taps, bool fma, in
         case 5: return rx_fast_launch_t<64, 0, false, false, 128, 6, 4, 3, 64>(a, h_taps, stream);
         case 6: return rx_fast_launch_t<64, 0, false, false, 128, 6, 4, 3, 32>(a, h_taps, stream);
         case 7: return rx_fast_launch_t<64, 0, false, false, 64, 11, 4, 3, 32>(a, h_taps, stream);
+        case 8: return rx_fast_launch_t<64, 0, false, false, 64, 7, 4, 3, 64>(a, h_taps, stream);
+        case 9: return rx_fast_launch_t<64, 0, false, false, 64, 6, 4, 3, 64>(a, h_taps, stream);
         default: break;
         }
     }

@@ -152,3 +152,20 @@ def test_create_rejects_bad_cfg(pkg):
     cfg.bits_per_symbol = 9
     assert L.modem_gpu_create(C.byref(ctx), 0, C.byref(cfg)) == -1
     assert b"bits_per_symbol" in L.modem_gpu_last_error(None)
+
+
+def test_hot_kernels_do_not_spill(pkg):
+    """The tuned RX kernel sits at its register cap (128 at 8 CTAs/SM): an innocent change to the argument structs
+    once cost 8 bytes of spill and 7 % of its speed.  The ptxas log of the in-tree build is the guard."""
+    logdir = os.path.join(ROOT, "rust-modem_b200", "lib")
+    hot = {"rx_fast_64.ptxas.log": "_ZN2mg14rx_fast_kernelILi64ELi0ELb0ELb0ELi64ELi8ELi4ELi3ELi64EEE",
+           "tx_fast.ptxas.log": "_ZN2mg19tx_rect_fast_kernelILi2ELb0EEE"}
+    for fn, sym in hot.items():
+        path = os.path.join(logdir, fn)
+        if not os.path.exists(path):
+            pytest.skip("library was not built here")
+        lines = open(path).read().splitlines()
+        idx = [i for i, l in enumerate(lines) if "Compiling entry function" in l and sym in l]
+        assert idx, (fn, sym)
+        block = " ".join(lines[idx[0]: idx[0] + 4])
+        assert "0 bytes spill stores, 0 bytes spill loads" in block, block

@@ -18,14 +18,19 @@ SPS, BPS, NSYM = 8, 2, 8192
 NBITS, L = NSYM * BPS, NSYM * SPS
 
 
-def run(name, F, shaped, flags=0, sigma_db=None, channels=0, steps=5):
+def run(name, F, shaped, flags=0, sigma_db=None, channels=0, steps=5, sps=8):
+    global SPS, NSYM, NBITS, L
+    SPS = sps
+    NSYM = 65536 // sps
+    NBITS, L = NSYM * BPS, NSYM * SPS
     lp = pkg.lowpass_taps()
     if shaped:
         rrc = pkg.rrc_taps(16, 8, 0.35)
         kw = dict(tx_taps=rrc, rx_taps=rrc, decision_delay=128, slicer_gain=1.0)
     else:
-        kw = dict(rx_taps=lp, decision_delay=35, slicer_gain=float(np.float32(lp.sum())))
-    m = pkg.Modem(scheme="qpsk", baud_rate=1250, sample_rate=10000, carrier_hz=2500, flags=flags, **kw)
+        kw = dict(rx_taps=lp, decision_delay=31 + sps // 2, slicer_gain=float(np.float32(lp.sum())))
+    br = {8: 1250, 45: 220}[sps]
+    m = pkg.Modem(scheme="qpsk", baud_rate=br, sample_rate=10000, carrier_hz=2500 if sps == 8 else 1000, flags=flags, **kw)
     st = torch.cuda.current_stream()
     m.set_stream(st.cuda_stream)
     if channels:
@@ -53,8 +58,8 @@ def run(name, F, shaped, flags=0, sigma_db=None, channels=0, steps=5):
     n = F * L
     res = {"config": name, "frames": F, "tx_ms": round(tx_ms, 4), "rx_ms": round(rx_ms, 4),
            "loopback_Msamples_s": round(n / (tx_ms + rx_ms) / 1e3, 0),
-           "tx_GBs": round(n * 8.25 / tx_ms / 1e6, 0), "tx_frac": round(n * 8.25 / tx_ms / 1e6 / PEAK, 3),
-           "rx_GBs": round(n * 8.625 / rx_ms / 1e6, 0), "rx_frac": round(n * 8.625 / rx_ms / 1e6 / PEAK, 3),
+           "tx_GBs": round(n * (8 + BPS / SPS) / tx_ms / 1e6, 0), "tx_frac": round(n * (8 + BPS / SPS) / tx_ms / 1e6 / PEAK, 3),
+           "rx_GBs": round(n * (8 + (1 + 2 * BPS) / SPS) / rx_ms / 1e6, 0), "rx_frac": round(n * (8 + (1 + 2 * BPS) / SPS) / rx_ms / 1e6 / PEAK, 3),
            "errors": int(cnt[0]), "bits": int(cnt[1]), "ber": float(cnt[0]) / max(int(cnt[1]), 1)}
     print(json.dumps(res), flush=True)
     m.close()
@@ -66,6 +71,7 @@ if __name__ == "__main__":
     which = sys.argv[1:] or ["c2", "c2f", "c3", "c3f", "c2n", "c3n", "c5"]
     FUSED = pkg.FLAG_FUSED_MAC
     for w in which:
+        if w == "c1": run("C1 rates (sr 10000 / baud 220 -> sps 45, 1000 Hz), 4096 frames x 65520 samples, generic kernels", 4096, False, sps=45)
         if w == "c2": run("C2 rect+lp64 exact", 4096, False)
         if w == "c2f": run("C2 rect+lp64 fused-MAC", 4096, False, flags=FUSED)
         if w == "c3": run("C3 rrc129 exact (16384 frames = 2^30 samples)", 16384, True, steps=3)
