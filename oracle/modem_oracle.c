@@ -669,11 +669,15 @@ void orc_awgn_sample(uint64_t seed, uint64_t frame, uint64_t n, float sigma, flo
     uint32_t key[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)};
     uint32_t r[4];
     orc_philox4x32_10(ctr, key, r);
-    float n0, n1;
-    if (n & 1) orc_box_muller(r[2], r[3], &n0, &n1);
-    else orc_box_muller(r[0], r[1], &n0, &n1);
-    *re = *re + sigma * n0;
-    *im = *im + sigma * n1;
+    /* one Philox block serves the aligned sample pair (2m, 2m+1): words 0,1 -> one Box-Muller pair whose cosine
+     * branch is the REAL-part noise of sample 2m and whose sine branch that of sample 2m+1; words 2,3 likewise
+     * for the imaginary parts.  (The demodulator only reads real parts, demodulator.rs:45-48: this way one
+     * logarithm, one square root and one sincos cover two samples.) */
+    float a0, a1, b0, b1;
+    orc_box_muller(r[0], r[1], &a0, &a1);
+    orc_box_muller(r[2], r[3], &b0, &b1);
+    *re = *re + sigma * ((n & 1) ? a1 : a0);
+    *im = *im + sigma * ((n & 1) ? b1 : b0);
 }
 void orc_awgn(float* buf, size_t F, size_t L, float sigma, uint64_t seed, uint64_t frame0)
 {

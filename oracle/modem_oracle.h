@@ -187,8 +187,9 @@ float orc_u01(uint32_t r);
 /* Box-Muller: n0 = r*cos(t), n1 = r*sin(t), r = sqrtf(-2*logf(u1)), t = 2pi*u2 */
 void orc_box_muller(uint32_t r0, uint32_t r1, float* n0, float* n1);
 /* complex AWGN for sample n of global frame `frame`:  counter = (n/2 lo, n/2 hi,
- * frame lo, frame hi), key = (seed lo, seed hi); even n uses words 0,1, odd n 2,3.
- * re += sigma*n0, im += sigma*n1. */
+ * frame lo, frame hi), key = (seed lo, seed hi).  Words 0,1 -> Box-Muller (a0, a1): the real-part
+ * noise of samples 2m and 2m+1; words 2,3 -> (b0, b1): their imaginary-part noise.
+ * re += sigma*a[n&1], im += sigma*b[n&1]. */
 void orc_awgn_sample(uint64_t seed, uint64_t frame, uint64_t n, float sigma, float* re, float* im);
 void orc_awgn(float* buf /*[F][L][2]*/, size_t F, size_t L, float sigma, uint64_t seed, uint64_t frame0);
 

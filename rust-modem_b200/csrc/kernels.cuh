@@ -196,16 +196,17 @@ __global__ void __launch_bounds__(kThreads) awgn_kernel(float2* buf, u64 F, u64 
         uint32_t r[4];
         philox4x32_10((uint32_t)pair, (uint32_t)(pair >> 32), (uint32_t)gf, (uint32_t)(gf >> 32),
                       (uint32_t)nz.seed, (uint32_t)(nz.seed >> 32), r);
+        float a[2], b[2];
+        box_muller(r[0], r[1], &a[0], &a[1]); /* real parts of samples 2m, 2m+1 */
+        box_muller(r[2], r[3], &b[0], &b[1]); /* imaginary parts */
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
             const u64 n = pair * 2 + e;
             if (n >= L) break;
-            float n0, n1;
-            box_muller(r[2 * e], r[2 * e + 1], &n0, &n1);
             float2* p = buf + f * L + n;
             float2 v = *p;
-            v.x = __fadd_rn(v.x, __fmul_rn(nz.sigma, n0));
-            v.y = __fadd_rn(v.y, __fmul_rn(nz.sigma, n1));
+            v.x = __fadd_rn(v.x, __fmul_rn(nz.sigma, a[e]));
+            v.y = __fadd_rn(v.y, __fmul_rn(nz.sigma, b[e]));
             *p = v;
         }
     }

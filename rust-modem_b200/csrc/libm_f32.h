@@ -179,6 +179,20 @@ MG_HD void mg_sincosf(float y, float* sinp, float* cosp)
     }
 }
 
+/* sinf / cosf for 0 <= y <= 7 without the magnitude dispatch: the pi/2 reduction branch of the routine above also
+ * reproduces glibc for |y| < pi/4 (n = 0) and for |y| < 2^-12 (the polynomials round to y and 1.0f there) --
+ * tools/check_libm.c sweeps every binary32 in [0, 7]: 0 mismatches.  Used where the argument is known to lie in
+ * (0, 2 pi] (Box-Muller's angle): no branches, one copy of the polynomial in the instruction stream. */
+MG_HD void mg_sincosf_0_7(float y, float* sinp, float* cosp)
+{
+    double x = (double)y;
+    double r = MG_DMUL(x, MG_HPI_INV_2P24);
+    int n = ((int32_t)r + 0x800000) >> 24;
+    x = MG_DFMA(-(double)n, MG_HPI, x);
+    double s = ((n & 3) == 1 || (n & 3) == 2) ? -1.0 : 1.0;
+    mg_sincos_poly(MG_DMUL(x, s), MG_DMUL(x, x), (n & 2) != 0, n, sinp, cosp);
+}
+
 /* ---- logf ------------------------------------------------------------------ */
 #define MG_LOGF_TAB_INIT { \
     {0x1.661ec79f8f3bep+0, -0x1.57bf7808caadep-2}, {0x1.571ed4aaf883dp+0, -0x1.2bef0a7c06ddbp-2}, \

@@ -265,22 +265,32 @@ __global__ void __launch_bounds__(THREADS, MINB)
         /* ---- phase A: load the tile (all loads issued before the first use), mix, stage */
         if (PF != 2) load_tile(frame);
         if (NOISE) {
+            /* G chunks per trip: their Philox / logf / sqrt / sincos chains are independent, so the scheduler can
+             * interleave them (one chunk per trip left ~2 independent chains per warp at 4 warps per scheduler:
+             * latency-bound); the trip count stays rolled to keep the code in the instruction cache */
+            constexpr int G = 4;
             const u64 gf = a.nz.frame0 + f;
 #pragma unroll 1
-            for (int it = 0; it < C::ITER; ++it) {
-                const long long n = nbase + 2 * (it * THREADS + tid);
-                if (it * THREADS + tid < C::NCHUNK) {
-                    float n0 = 0.0f, n1 = 0.0f;
-                    const bool v0 = n >= vlo_n && n < vhi_n, v1 = v0;
-                    if (v0) noise_re_pair(a.nz, gf, (u64)n, &n0, &n1); /* n is even: one Philox block per pair */
-                    /* xr[] must be indexed statically to stay in registers */
+            for (int it0 = 0; it0 < C::ITER; it0 += G) {
+                float n0[G], n1[G];
+                bool v[G];
 #pragma unroll
-                    for (int j = 0; j < C::ITER; ++j)
-                        if (j == it) {
-                            if (v0) xr[j][0] = __fadd_rn(xr[j][0], __fmul_rn(a.nz.sigma, n0));
-                            if (v1) xr[j][1] = __fadd_rn(xr[j][1], __fmul_rn(a.nz.sigma, n1));
-                        }
+                for (int g = 0; g < G; ++g) {
+                    const int it = it0 + g;
+                    const long long n = nbase + 2 * (it * THREADS + tid);
+                    n0[g] = n1[g] = 0.0f;
+                    v[g] = it < C::ITER && it * THREADS + tid < C::NCHUNK && n >= vlo_n && n < vhi_n;
+                    if (v[g]) noise_re_pair(a.nz, gf, (u64)n, &n0[g], &n1[g]); /* n is even: one Philox block per pair */
                 }
+                /* xr[] must be indexed statically to stay in registers */
+#pragma unroll
+                for (int j = 0; j < C::ITER; ++j)
+#pragma unroll
+                    for (int g = 0; g < G; ++g)
+                        if (j == it0 + g && v[g]) {
+                            xr[j][0] = __fadd_rn(xr[j][0], __fmul_rn(a.nz.sigma, n0[g]));
+                            xr[j][1] = __fadd_rn(xr[j][1], __fmul_rn(a.nz.sigma, n1[g]));
+                        }
             }
         }
         float parked[TMC > 0 ? TMC : 4];

@@ -42,6 +42,9 @@ cudaError_t rx_fast_launch_129(const RxArgs& a, const float* h_taps, bool fma, i
         default: break;
         }
     }
+    /* the noisy variants carry the Philox / Box-Muller state on top of the FIR's registers: give them the roomier
+     * 8-CTA shape (the 10-CTA shape spills 80 bytes there) */
+    if (a.nz.sigma != 0.0f) return rx_fast_dispatch<129, 64, 8, 4, RX_DEFAULT_PF, 64>(a, h_taps, fma, stream);
     return rx_fast_dispatch<129, RX129_THREADS, RX129_MINB, RX129_R, RX_DEFAULT_PF, RX129_TMC>(a, h_taps, fma, stream);
 }
 uint64_t rx_fast_tiles_129(uint64_t K, int variant)

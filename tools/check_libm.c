@@ -47,6 +47,18 @@ int main(int argc, char** argv)
         n_trig++;
     }
     printf("sincosf: %ld inputs, sin mismatches %ld, cos mismatches %ld\n", n_trig, bad_sin, bad_cos);
+    {
+        long bad07 = 0, n07 = 0;
+        const uint32_t top = mg_asuint_host(7.0f);
+#pragma omp parallel for reduction(+ : bad07, n07) schedule(static)
+        for (uint32_t u = 0; u <= top; ++u) {
+            float y = asf(u), s, c;
+            mg_sincosf_0_7(y, &s, &c);
+            bad07 += mg_asuint_host(s) != mg_asuint_host(sinf(y)) || mg_asuint_host(c) != mg_asuint_host(cosf(y));
+            n07++;
+        }
+        printf("sincosf_0_7 (branch-free form, every binary32 in [0, 7]): %ld inputs, %ld mismatches\n", n07, bad07);
+    }
 
 #pragma omp parallel for reduction(+ : bad_log, n_log) schedule(static)
     for (uint32_t u = 1; u <= 0x3f800000u; ++u) {
