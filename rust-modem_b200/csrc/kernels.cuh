@@ -261,33 +261,55 @@ __global__ void __launch_bounds__(kThreads) rx_generic_kernel(const __grid_const
     for (u64 f = f0; f < f1; ++f) {
         const float pof = pfp ? chan_po(a.ch, f) : 0.0f;
         __syncthreads();
-        for (uint32_t j = threadIdx.x; j < R; j += kThreads) {
-            long long n = nb + j;
-            float2 v = make_float2(0.0f, 0.0f);
-            if (n >= 0 && (u64)n < a.L) {
-                float2 cs = s_cs[j];
-                if (pfp) mg_sincosf(__fadd_rn(cs.x, pof), &cs.y, &cs.x);
-                v = rx_mix(a, f, a.nz.frame0 + f, (u64)n, cs.x, cs.y);
+        /* staging, four samples per thread and trip with the global loads issued first: a rolled one-sample loop
+         * exposes the full DRAM latency once per sample (measured: 2.7 ms at the reference's sps 45) */
+        for (uint32_t j0 = threadIdx.x; j0 < R; j0 += 4 * kThreads) {
+            float x[4];
+            bool ok[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const uint32_t j = j0 + u * kThreads;
+                const long long n = nb + j;
+                ok[u] = j < R && n >= 0 && (u64)n < a.L;
+                x[u] = ok[u] ? rx_sample(a, f, (u64)n) : 0.0f;
             }
-            s_vi[rx_generic_skew(j)] = v.x;
-            s_vq[rx_generic_skew(j)] = v.y;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const uint32_t j = j0 + u * kThreads;
+                if (j >= R) break;
+                float2 v = make_float2(0.0f, 0.0f);
+                if (ok[u]) {
+                    float2 cs = s_cs[j];
+                    if (pfp) mg_sincosf(__fadd_rn(cs.x, pof), &cs.y, &cs.x);
+                    float xv = x[u];
+                    if (a.nz.sigma != 0.0f) xv = __fadd_rn(xv, __fmul_rn(a.nz.sigma, noise_re(a.nz, a.nz.frame0 + f, (u64)(nb + j))));
+                    v = make_float2(__fmul_rn(xv, cs.x), __fmul_rn(xv, -cs.y)); /* demodulator.rs:53-54 */
+                }
+                s_vi[rx_generic_skew(j)] = v.x;
+                s_vq[rx_generic_skew(j)] = v.y;
+            }
         }
         __syncthreads();
-        for (uint32_t t = threadIdx.x; t < TS; t += kThreads) {
+        /* one thread per (symbol, rail): even lanes fold the I rail, odd lanes the Q rail of the same symbol (each
+         * fold is an ordered chain of N dependent MACs, fir.rs:21-24 -- two chains per symbol run side by side),
+         * then the pair meets through one shuffle and the even lane slices */
+        for (uint32_t t2 = threadIdx.x; t2 < ((2 * TS + 31) & ~31u); t2 += kThreads) {
+            const uint32_t t = t2 >> 1, rail = t2 & 1u;
             const u64 k = k0 + t;
-            if (k >= a.K) break;
-            const uint32_t ji = t * sps + (N - 1); /* local index of n_k */
-            const uint32_t jq = ji + a.q_offset;
-            float ai = 0.0f, aq = 0.0f;
-            for (uint32_t i = 0; i < N; ++i) {
-                float c = s_taps[i];
-                ai = mac<FMA>(ai, s_vi[rx_generic_skew(ji - i)], c);
-                aq = mac<FMA>(aq, s_vq[rx_generic_skew(jq - i)], c);
+            const bool live = t < TS && k < a.K;
+            float acc = 0.0f;
+            if (live) {
+                const float* sv = rail ? s_vq : s_vi;
+                const uint32_t j = t * sps + (N - 1) + (rail ? a.q_offset : 0u); /* local index of n_k (+ Q lag) */
+                for (uint32_t i = 0; i < N; ++i) acc = mac<FMA>(acc, sv[rx_generic_skew(j - i)], s_taps[i]);
             }
-            const float I = __fmul_rn(a.rx_gain, ai), Q = __fmul_rn(a.rx_gain, aq);
-            const uint32_t s = slice_point(s_slut + (k % a.n_tables) * a.n_const, a.n_const, I, Q);
-            err += emit_symbol(a, f, k, s, I, Q);
-            cmp += a.ref_bits ? a.bps : 0u;
+            const float other = __shfl_xor_sync(0xffffffffu, acc, 1);
+            if (live && rail == 0) {
+                const float I = __fmul_rn(a.rx_gain, acc), Q = __fmul_rn(a.rx_gain, other);
+                const uint32_t s = slice_point(s_slut + (k % a.n_tables) * a.n_const, a.n_const, I, Q);
+                err += emit_symbol(a, f, k, s, I, Q);
+                cmp += a.ref_bits ? a.bps : 0u;
+            }
         }
     }
     block_count(a, err, cmp);

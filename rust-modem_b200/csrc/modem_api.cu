@@ -459,11 +459,14 @@ int launch_rx(modem_ctx* ctx, const float2* d_rx, u64 F, u64 L, uint8_t* d_sym, 
         if (!a.ch.cs_tab) return fail(ctx, MODEM_ERR_UNSUPPORTED, "carrier bank too large for the NCO table (> 1 GiB)");
         CK(ctx, mg::rx_fast_launch(a, ctx->h_rx_taps.data(), fma, ctx->rx_variant, ctx->stream));
     } else {
-        const size_t budget = 96 * 1024;
+        size_t budget = 96 * 1024;
         if ((size_t)N * 4 + (size_t)(N + c.q_offset) * 17 + 64 > budget)
             return fail(ctx, MODEM_ERR_UNSUPPORTED, "rx_taps too long for shared memory");
+        /* up to 128 symbols x 2 rails keep all 256 threads busy in the FIR; tiles of <= 48 KB leave room for 4 CTAs
+         * per SM so that one CTA's staging overlaps another's FIR (long filters may need more for a useful tile) */
+        budget = std::min<size_t>(budget, std::max<size_t>(48 * 1024, (size_t)N * 4 + 64 + 17 * ((size_t)15 * sps + N + c.q_offset)));
         const size_t rmax = (budget - (size_t)N * 4 - 64) / 17; /* 8 B of NCO + 2 skewed rails (4 + 1/8 B each) per staged sample */
-        uint32_t TS = (uint32_t)std::min<size_t>(256, (rmax - N - c.q_offset) / sps + 1);
+        uint32_t TS = (uint32_t)std::min<size_t>(128, (rmax - N - c.q_offset) / sps + 1);
         TS = std::max<uint32_t>(TS, 1);
         a.sym_tile = TS;
         const size_t R = (size_t)(TS - 1) * sps + N + c.q_offset;
