@@ -318,7 +318,7 @@ int launch_tx(modem_ctx* ctx, const uint8_t* d_bits, u64 F, u64 nbits, float2* d
         const uint32_t bps = c.bits_per_symbol;
         const bool word_ok = mg::tx_rect_fast_supported(bps) && (nbits % bps == 0) &&
                              ((reinterpret_cast<uintptr_t>(d_bits) % bps) == 0);
-        const bool fast_shape = !ctx->force_generic && !d_iq && c.q_offset == 0 && c.n_tables == 1 && (c.samples_per_symbol % 2 == 0) &&
+        const bool fast_shape = !ctx->force_generic && !d_iq && c.q_offset == 0 && c.n_tables == 1 &&
                                 word_ok && a.L < (1ull << 32) && (a.L % 2 == 0);
         const bool fast = fast_shape && ((plain && vec_ok && d_tx) || (ro && ro->re && !d_tx));
         if (fast) {

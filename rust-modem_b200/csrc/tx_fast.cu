@@ -14,7 +14,9 @@ namespace mg {
  * with all bit loads of the batch issued first, so FU*U independent loads are in flight
  * per thread instead of one dependent chain per frame.
  */
-template <int BPS, bool REAL>
+/* TWO: odd samples-per-symbol (the reference's default rates give 45): the two samples of a store may belong to
+ * different symbols, so each gets its own bit word and table lookup */
+template <int BPS, bool REAL, bool TWO>
 __global__ void __launch_bounds__(kThreads, 4) tx_rect_fast_kernel(const __grid_constant__ TxArgs a)
 {
     constexpr int U = 2, FU = 4;
@@ -28,6 +30,7 @@ __global__ void __launch_bounds__(kThreads, 4) tx_rect_fast_kernel(const __grid_
     const float2* tab = chan_table(a.ch, f0);
 
     uint32_t koff[U]; /* byte offset of the symbol's bits inside a frame row */
+    uint32_t koff1[U]; /* TWO: the same for the pair's second sample */
     uint32_t noff[U]; /* float4 offset of the sample pair inside a frame row */
     bool valid[U];
     float c0[U], s0[U], c1[U], s1[U];
@@ -38,6 +41,7 @@ __global__ void __launch_bounds__(kThreads, 4) tx_rect_fast_kernel(const __grid_
         valid[u] = n < a.L;
         noff[u] = pair;
         koff[u] = (uint32_t)(n / a.sps) * BPS;
+        koff1[u] = TWO ? (uint32_t)((n + 1) / a.sps) * BPS : koff[u];
         if (tab && n + 1 < a.L) { /* n is even and the table row is 16-byte aligned */
             const float4 t = __ldg(reinterpret_cast<const float4*>(tab + n));
             c0[u] = t.x; s0[u] = t.y; c1[u] = t.z; s1[u] = t.w;
@@ -64,18 +68,22 @@ __global__ void __launch_bounds__(kThreads, 4) tx_rect_fast_kernel(const __grid_
     };
     u64 f = f0;
     for (; f + FU <= f1; f += FU) {
-        uint32_t idx[FU][U];
+        uint32_t idx[FU][U], idx1[FU][U];
 #pragma unroll
         for (int j = 0; j < FU; ++j)
 #pragma unroll
-            for (int u = 0; u < U; ++u) idx[j][u] = valid[u] ? load_symbol_word<BPS>(pb + j * a.nbits + koff[u]) : 0u;
+            for (int u = 0; u < U; ++u) {
+                idx[j][u] = valid[u] ? load_symbol_word<BPS>(pb + j * a.nbits + koff[u]) : 0u;
+                idx1[j][u] = TWO ? (valid[u] ? load_symbol_word<BPS>(pb + j * a.nbits + koff1[u]) : 0u) : idx[j][u];
+            }
 #pragma unroll
         for (int j = 0; j < FU; ++j)
 #pragma unroll
             for (int u = 0; u < U; ++u) {
                 const float2 bb = s_lut[idx[j][u]];
+                const float2 b1 = TWO ? s_lut[idx1[j][u]] : bb;
                 const float2 o0 = mix_iq(bb.x, bb.y, c0[u], s0[u]);
-                const float2 o1 = mix_iq(bb.x, bb.y, c1[u], s1[u]);
+                const float2 o1 = mix_iq(b1.x, b1.y, c1[u], s1[u]);
                 if (valid[u]) emit(j, u, o0, o1);
             }
         pb += FU * a.nbits;
@@ -87,8 +95,9 @@ __global__ void __launch_bounds__(kThreads, 4) tx_rect_fast_kernel(const __grid_
         for (int u = 0; u < U; ++u) {
             if (!valid[u]) continue;
             const float2 bb = s_lut[load_symbol_word<BPS>(pb + koff[u])];
+            const float2 b1 = TWO ? s_lut[load_symbol_word<BPS>(pb + koff1[u])] : bb;
             const float2 o0 = mix_iq(bb.x, bb.y, c0[u], s0[u]);
-            const float2 o1 = mix_iq(bb.x, bb.y, c1[u], s1[u]);
+            const float2 o1 = mix_iq(b1.x, b1.y, c1[u], s1[u]);
             emit(0, u, o0, o1);
         }
         pb += a.nbits;
@@ -221,21 +230,24 @@ uint64_t tx_rect_fast_tiles(uint64_t L) { return (L + 4 * kThreads - 1) / (4 * k
 cudaError_t tx_rect_fast_launch(const TxArgs& a, cudaStream_t stream)
 {
     dim3 grid((unsigned)tx_rect_fast_tiles(a.L), (unsigned)((a.F + a.frames_per_block - 1) / a.frames_per_block));
-    if (a.re && !a.tx) {
-        switch (a.bps) {
-        case 1: tx_rect_fast_kernel<1, true><<<grid, kThreads, 0, stream>>>(a); break;
-        case 2: tx_rect_fast_kernel<2, true><<<grid, kThreads, 0, stream>>>(a); break;
-        case 4: tx_rect_fast_kernel<4, true><<<grid, kThreads, 0, stream>>>(a); break;
-        default: tx_rect_fast_kernel<8, true><<<grid, kThreads, 0, stream>>>(a); break;
-        }
-        return cudaGetLastError();
-    }
+    const bool real = a.re && !a.tx, two = (a.sps & 1u) != 0;
+#define MG_TXR(B)                                                                              \
+    do {                                                                                       \
+        if (real) {                                                                            \
+            if (two) tx_rect_fast_kernel<B, true, true><<<grid, kThreads, 0, stream>>>(a);     \
+            else tx_rect_fast_kernel<B, true, false><<<grid, kThreads, 0, stream>>>(a);        \
+        } else {                                                                               \
+            if (two) tx_rect_fast_kernel<B, false, true><<<grid, kThreads, 0, stream>>>(a);    \
+            else tx_rect_fast_kernel<B, false, false><<<grid, kThreads, 0, stream>>>(a);       \
+        }                                                                                      \
+    } while (0)
     switch (a.bps) {
-    case 1: tx_rect_fast_kernel<1, false><<<grid, kThreads, 0, stream>>>(a); break;
-    case 2: tx_rect_fast_kernel<2, false><<<grid, kThreads, 0, stream>>>(a); break;
-    case 4: tx_rect_fast_kernel<4, false><<<grid, kThreads, 0, stream>>>(a); break;
-    default: tx_rect_fast_kernel<8, false><<<grid, kThreads, 0, stream>>>(a); break;
+    case 1: MG_TXR(1); break;
+    case 2: MG_TXR(2); break;
+    case 4: MG_TXR(4); break;
+    default: MG_TXR(8); break;
     }
+#undef MG_TXR
     return cudaGetLastError();
 }
 

@@ -159,7 +159,7 @@ def test_hot_kernels_do_not_spill(pkg):
     once cost 8 bytes of spill and 7 % of its speed.  The ptxas log of the in-tree build is the guard."""
     logdir = os.path.join(ROOT, "rust-modem_b200", "lib")
     hot = {"rx_fast_64.ptxas.log": "_ZN2mg14rx_fast_kernelILi64ELi0ELb0ELb0ELi64ELi8ELi4ELi3ELi64EEE",
-           "tx_fast.ptxas.log": "_ZN2mg19tx_rect_fast_kernelILi2ELb0EEE"}
+           "tx_fast.ptxas.log": "_ZN2mg19tx_rect_fast_kernelILi2ELb0ELb0EEE"}
     for fn, sym in hot.items():
         path = os.path.join(logdir, fn)
         if not os.path.exists(path):

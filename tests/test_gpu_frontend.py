@@ -83,6 +83,18 @@ def test_modulate_real_fast_kernel(pkg, orc, scheme, preamble):
     assert_buffers(m.modulate(bits), o.modulate(bits), f"{scheme} complex output after a real call")
 
 
+@pytest.mark.parametrize("scheme,sps", [("qpsk", 45), ("qam16", 45), ("bpsk", 45)])
+def test_tx_fast_kernel_odd_sps(pkg, orc, scheme, sps):
+    """The reference's default rates (sps 45): the two samples of a 128-bit store straddle symbol edges; both the
+    complex and the real-output form of the tuned kernel (even frame length)."""
+    kw = dict(scheme=scheme, baud_rate=220, sample_rate=10000, carrier_hz=1000)
+    m, o = pkg.Modem(**kw), orc.OraclePath(**kw)
+    bits = rand_bits(34, 9, 146 * o.bps)
+    assert o.frame_samples(bits.shape[1]) % 2 == 0
+    assert_buffers(m.modulate(bits), o.modulate(bits), f"{scheme} sps {sps} tx")
+    assert_buffers(m.modulate_real(bits, preamble=19), o.modulate_real(bits, preamble=19), f"{scheme} sps {sps} real output")
+
+
 def test_modulate_real_shaped(pkg, orc):
     rrc = orc.rrc_taps(16, 8, 0.35)
     kw = dict(scheme="qpsk", baud_rate=1250, sample_rate=10000, carrier_hz=2500, tx_taps=rrc, rx_taps=rrc,
