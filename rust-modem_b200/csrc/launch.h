@@ -31,6 +31,6 @@ uint64_t tx_rect_fast_tiles(uint64_t L);
 cudaError_t tx_rect_fast_launch(const TxArgs& a, cudaStream_t stream);
 bool tx_shaped_fast_supported(uint32_t sps, uint32_t n_taps);
 uint64_t tx_shaped_fast_tiles(uint64_t nsym);
-cudaError_t tx_shaped_fast_launch(const TxArgs& a, const float* h_taps, bool fma, cudaStream_t stream);
+cudaError_t tx_shaped_fast_launch(const TxArgs& a, const float* h_taps, bool fma, bool rail_pairs, cudaStream_t stream);
 
 } /* namespace mg */

@@ -10,6 +10,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <cmath>
 #include <string>
 #include <vector>
 
@@ -37,6 +38,13 @@ struct modem_ctx {
     modem_cfg_t cfg{};
     std::vector<float> h_const, h_slut, h_tx_taps, h_rx_taps;
     float2* d_lut = nullptr;
+    /* sign-product form of the shaped TX: every constellation point is (+-vi, +-vq) with one magnitude per rail, so
+     * round(h[k] * (+-v)) = +-round(h[k] * v) is a per-tap constant and the reference's multiply-round-add-round of
+     * fir.rs:21-24 becomes ONE fma(+-1, round(h[k] * v), acc) -- the product by +-1 is exact, so the single rounding
+     * of the fma is the reference's rounding of the add: bit-identical with half the FP32 lane work */
+    float2* d_sign_lut = nullptr;
+    std::vector<float> h_tx_rail_taps; /* (round(h[k] * vi), round(h[k] * vq)) pairs */
+    bool tx_sign_form = false;
     float2* d_slut = nullptr;
     float* d_tx_taps = nullptr;
     float* d_rx_taps = nullptr;
@@ -58,12 +66,19 @@ struct modem_ctx {
             return L == o.L && sample0 == o.sample0 && deviation == o.deviation && amplitude == o.amplitude && bps == o.bps;
         }
     } cp_key;
-    /* host-buffer loopback pipeline: three lanes, each with its own stream and chunk buffers */
+    /* host-buffer loopback pipeline: three streams by role (lanes[0] copies in, lanes[1] runs the kernels,
+     * lanes[2] copies out) over a ring of chunk slots; the TX samples of a chunk never leave the kernel stream,
+     * so one chunk-sized sample buffer serves every slot */
     struct Lane {
         cudaStream_t s = nullptr;
         cudaEvent_t done = nullptr;
-        Scratch bits, tx, sym, out;
     } lanes[3];
+    static constexpr int kPipeSlots = 4;
+    struct Slot {
+        cudaEvent_t in_done = nullptr, comp_done = nullptr, out_done = nullptr;
+        Scratch bits, sym, out;
+    } slots[kPipeSlots];
+    Scratch pipe_tx;
     bool lanes_ready = false;
     cudaEvent_t ev_start = nullptr;
     u64 frame_base = 0; /* see ChannelView::frame_base */
@@ -340,7 +355,12 @@ int launch_tx(modem_ctx* ctx, const uint8_t* d_bits, u64 F, u64 nbits, float2* d
         a.frames_per_block = frames_per_block(ctx, F, mg::tx_shaped_fast_tiles(a.nsym));
         int rc = attach_carrier_table(ctx, a.ch, F, a.L, false);
         if (rc) return rc;
-        CK(ctx, mg::tx_shaped_fast_launch(a, ctx->h_tx_taps.data(), fma, ctx->stream));
+        if (ctx->tx_sign_form && !fma) { /* exact, one FFMA2 per tap pair instead of FMUL2 + FFMA2 */
+            a.lut = ctx->d_sign_lut;
+            CK(ctx, mg::tx_shaped_fast_launch(a, ctx->h_tx_rail_taps.data(), true, true, ctx->stream));
+        } else {
+            CK(ctx, mg::tx_shaped_fast_launch(a, ctx->h_tx_taps.data(), fma, false, ctx->stream));
+        }
     } else {
         const uint32_t sps = c.samples_per_symbol, N = c.n_tx_taps;
         uint32_t TS = std::max<uint32_t>(1, std::min<uint32_t>(256, 2048 / sps));
@@ -705,6 +725,28 @@ int modem_gpu_create(modem_ctx_t** out, int device, const modem_cfg_t* cfg)
     }
     ctx->h_rx_taps.assign(cfg->rx_taps, cfg->rx_taps + cfg->n_rx_taps);
     if (cfg->n_tx_taps) ctx->h_tx_taps.assign(cfg->tx_taps, cfg->tx_taps + cfg->n_tx_taps);
+    std::vector<float> h_sign;
+    if (cfg->n_tx_taps && np) { /* sign-product form: one magnitude per rail over every table? */
+        auto mag = [](float v) { uint32_t u; memcpy(&u, &v, 4); u &= 0x7fffffffu; return u; };
+        const uint32_t mi = mag(ctx->h_const[0]), mq = mag(ctx->h_const[1]);
+        bool ok = true;
+        for (size_t i = 0; i < np && ok; ++i) ok = mag(ctx->h_const[2 * i]) == mi && mag(ctx->h_const[2 * i + 1]) == mq;
+        const char* ns = getenv("MODEM_GPU_NO_SIGN_FORM");
+        if (ok && !(ns && ns[0] == '1')) {
+            float vi, vq;
+            memcpy(&vi, &mi, 4);
+            memcpy(&vq, &mq, 4);
+            h_sign.resize(2 * np);
+            for (size_t i = 0; i < 2 * np; ++i) h_sign[i] = std::signbit(ctx->h_const[i]) ? -1.0f : 1.0f;
+            ctx->h_tx_rail_taps.resize(2 * (size_t)cfg->n_tx_taps);
+            for (uint32_t k = 0; k < cfg->n_tx_taps; ++k) {
+                volatile float pi = ctx->h_tx_taps[k] * vi, pq = ctx->h_tx_taps[k] * vq; /* one rounded binary32 product each */
+                ctx->h_tx_rail_taps[2 * k] = pi;
+                ctx->h_tx_rail_taps[2 * k + 1] = pq;
+            }
+            ctx->tx_sign_form = true;
+        }
+    }
     ctx->cfg.const_iq = ctx->h_const.data();
     ctx->cfg.rx_taps = ctx->h_rx_taps.data();
     ctx->cfg.tx_taps = cfg->n_tx_taps ? ctx->h_tx_taps.data() : nullptr;
@@ -730,6 +772,7 @@ int modem_gpu_create(modem_ctx_t** out, int device, const modem_cfg_t* cfg)
     ctx->own_stream = rc == MODEM_OK;
     if (!rc) rc = upload(ctx, (void**)&ctx->d_lut, ctx->h_const.data(), ctx->h_const.size() * 4);
     if (!rc) rc = upload(ctx, (void**)&ctx->d_slut, ctx->h_slut.data(), ctx->h_slut.size() * 4);
+    if (!rc && ctx->tx_sign_form) rc = upload(ctx, (void**)&ctx->d_sign_lut, h_sign.data(), h_sign.size() * 4);
     if (!rc) rc = upload(ctx, (void**)&ctx->d_rx_taps, ctx->h_rx_taps.data(), ctx->h_rx_taps.size() * 4);
     if (!rc && cfg->n_tx_taps) rc = upload(ctx, (void**)&ctx->d_tx_taps, ctx->h_tx_taps.data(), ctx->h_tx_taps.size() * 4);
     if (!rc) {
@@ -751,18 +794,23 @@ void modem_gpu_destroy(modem_ctx_t* ctx)
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
-    void* ptrs[] = {ctx->d_lut, ctx->d_slut, ctx->d_tx_taps, ctx->d_rx_taps, ctx->d_chan_w, ctx->d_chan_po, ctx->d_counters,
+    void* ptrs[] = {ctx->d_lut, ctx->d_sign_lut, ctx->d_slut, ctx->d_tx_taps, ctx->d_rx_taps, ctx->d_chan_w, ctx->d_chan_po, ctx->d_counters,
                     ctx->s_bits.p, ctx->s_tx.p, ctx->s_iq.p, ctx->s_rx.p, ctx->s_sym.p, ctx->s_bits_out.p, ctx->s_soft.p, ctx->s_filt.p,
                     ctx->s_state.p, ctx->s_re.p, ctx->s_raw.p, ctx->s_po.p, ctx->s_hilbert.p, ctx->s_siq.p, ctx->s_cptab.p};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     for (auto& ln : ctx->lanes) {
         if (ln.s) cudaStreamSynchronize(ln.s);
-        for (void* p : {ln.bits.p, ln.tx.p, ln.sym.p, ln.out.p})
-            if (p) cudaFree(p);
         if (ln.done) cudaEventDestroy(ln.done);
         if (ln.s) cudaStreamDestroy(ln.s);
     }
+    for (auto& sl : ctx->slots) {
+        for (void* p : {sl.bits.p, sl.sym.p, sl.out.p})
+            if (p) cudaFree(p);
+        for (cudaEvent_t e : {sl.in_done, sl.comp_done, sl.out_done})
+            if (e) cudaEventDestroy(e);
+    }
+    if (ctx->pipe_tx.p) cudaFree(ctx->pipe_tx.p);
     if (ctx->ev_start) cudaEventDestroy(ctx->ev_start);
     for (auto e : ctx->ev_pool)
         if (e) cudaEventDestroy(e);
@@ -1069,11 +1117,13 @@ int modem_gpu_demodulate_count(modem_ctx_t* ctx, const modem_c32_t* rx, size_t F
 
 namespace {
 /*
- * Host-buffer loopback, pipelined: the frames are cut into chunks that go round three lanes;
- * each lane runs H2D(bits) -> TX kernel -> RX kernel -> D2H(sym, bits) on its own stream, so
- * one lane's copies (two independent DMA directions) overlap another lane's kernels.  Chunks
- * carry ~128 MB of TX samples each (256 frames at 65536 samples): smaller chunks make the
- * per-chunk kernels inefficient (measured: 2.7 ms at 64 frames, 1.76 ms at 256..512 for C2).
+ * Host-buffer loopback, pipelined by role: lanes[0] issues every H2D(bits) back to back, lanes[1] runs
+ * TX kernel -> RX kernel chunk after chunk, lanes[2] issues every D2H(sym, bits); events hand a chunk from one
+ * stream to the next and return its slot of the ring when the consumer is done.  The H2D engine is the
+ * bottleneck of the step (as many bytes come back as go in, on the other DMA direction), and in this form it
+ * never waits for a chunk's kernels or its copy-out (the earlier lane-per-chunk form serialised
+ * H2D -> kernels -> D2H inside a lane and left the engine idle whenever a lane was late).  Chunks carry
+ * ~128 MB of TX samples (256 frames at 65536 samples): smaller chunks make the per-chunk kernels inefficient.
  */
 int loopback_pipelined(modem_ctx* ctx, const uint8_t* bits, size_t F, size_t nbits, float sigma, uint64_t seed,
                        uint64_t frame0, uint8_t* sym, uint8_t* bits_out, uint64_t counters[2], size_t Fc)
@@ -1089,44 +1139,66 @@ int loopback_pipelined(modem_ctx* ctx, const uint8_t* bits, size_t F, size_t nbi
         CK(ctx, cudaEventCreateWithFlags(&ctx->ev_start, cudaEventDisableTiming));
         ctx->lanes_ready = true;
     }
+    for (auto& sl : ctx->slots)
+        for (cudaEvent_t* e : {&sl.in_done, &sl.comp_done, &sl.out_done})
+            if (!*e) CK(ctx, cudaEventCreateWithFlags(e, cudaEventDisableTiming));
     CK(ctx, cudaMemsetAsync(ctx->d_counters, 0, 2 * sizeof(u64), ctx->stream));
     {
-        /* NCO tables for the whole call, built once before the lanes fork (they share the table buffers) */
+        /* NCO tables for the whole call, built once before the streams fork (every chunk shares them) */
         mg::ChannelView dummy = channel_view(ctx);
         int rc0 = attach_carrier_table(ctx, dummy, F, L, false);
         if (rc0) return rc0;
     }
+    int rc = ensure(ctx, ctx->pipe_tx, Fc * L * sizeof(float2));
+    for (auto& sl : ctx->slots) {
+        if (!rc) rc = ensure(ctx, sl.bits, Fc * nbits);
+        if (!rc && sym) rc = ensure(ctx, sl.sym, Fc * K);
+        if (!rc && bits_out) rc = ensure(ctx, sl.out, Fc * K * bps);
+    }
+    if (rc) return rc;
     CK(ctx, cudaEventRecord(ctx->ev_start, ctx->stream));
     for (auto& ln : ctx->lanes) CK(ctx, cudaStreamWaitEvent(ln.s, ctx->ev_start, 0));
 
     cudaStream_t user_stream = ctx->stream;
-    int rc = MODEM_OK;
+    cudaStream_t s_in = ctx->lanes[0].s, s_k = ctx->lanes[1].s, s_out = ctx->lanes[2].s;
+    const bool copies_out = K && (sym || bits_out);
+    cudaError_t e = cudaSuccess;
+    /* equal chunks: a ramped schedule (quarter and half chunks at both ends, to shorten the one copy-in and the
+     * one copy-out nothing overlaps) measured 1.667 ms against 1.641 ms -- the short kernels cost more than they save */
     size_t c = 0;
-    for (size_t fs = 0; fs < F && !rc; fs += Fc, ++c) {
+    for (size_t fs = 0; fs < F && !rc && e == cudaSuccess; fs += Fc, ++c) {
         const size_t n = std::min(Fc, F - fs);
-        auto& ln = ctx->lanes[c % 3];
-        rc = ensure(ctx, ln.bits, Fc * nbits);
-        if (!rc) rc = ensure(ctx, ln.tx, Fc * L * sizeof(float2));
-        if (!rc && sym) rc = ensure(ctx, ln.sym, Fc * K);
-        if (!rc && bits_out) rc = ensure(ctx, ln.out, Fc * K * bps);
-        if (rc) break;
-        ctx->stream = ln.s; /* launch_* enqueue on ctx->stream */
+        auto& sl = ctx->slots[c % modem_ctx::kPipeSlots];
+        const bool reused = c >= (size_t)modem_ctx::kPipeSlots;
+        /* copy in: the slot's bits are free once the RX kernel of its previous chunk has compared against them */
+        if (reused) e = cudaStreamWaitEvent(s_in, sl.comp_done, 0);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(sl.bits.p, bits + fs * nbits, n * nbits, cudaMemcpyHostToDevice, s_in);
+        if (e == cudaSuccess) e = cudaEventRecord(sl.in_done, s_in);
+        /* kernels: need this chunk's bits, and the slot's result buffers back from the previous copy-out */
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(s_k, sl.in_done, 0);
+        if (e == cudaSuccess && reused && copies_out) e = cudaStreamWaitEvent(s_k, sl.out_done, 0);
+        if (e != cudaSuccess) break;
+        ctx->stream = s_k; /* launch_* enqueue on ctx->stream */
         ctx->frame_base = fs;
-        cudaError_t e = cudaMemcpyAsync(ln.bits.p, bits + fs * nbits, n * nbits, cudaMemcpyHostToDevice, ln.s);
-        if (e == cudaSuccess) {
-            rc = launch_tx(ctx, (const uint8_t*)ln.bits.p, n, nbits, (float2*)ln.tx.p, nullptr);
-            if (!rc)
-                rc = launch_rx(ctx, (const float2*)ln.tx.p, n, L, sym ? (uint8_t*)ln.sym.p : nullptr,
-                               bits_out ? (uint8_t*)ln.out.p : nullptr, nullptr, nullptr, (const uint8_t*)ln.bits.p, nbits,
-                               ctx->d_counters, sigma, seed, frame0 + fs);
-            if (!rc && sym && K) e = cudaMemcpyAsync(sym + fs * K, ln.sym.p, n * K, cudaMemcpyDeviceToHost, ln.s);
-            if (!rc && e == cudaSuccess && bits_out && K)
-                e = cudaMemcpyAsync(bits_out + fs * K * bps, ln.out.p, n * K * bps, cudaMemcpyDeviceToHost, ln.s);
-        }
+        rc = launch_tx(ctx, (const uint8_t*)sl.bits.p, n, nbits, (float2*)ctx->pipe_tx.p, nullptr);
+        if (!rc)
+            rc = launch_rx(ctx, (const float2*)ctx->pipe_tx.p, n, L, sym ? (uint8_t*)sl.sym.p : nullptr,
+                           bits_out ? (uint8_t*)sl.out.p : nullptr, nullptr, nullptr, (const uint8_t*)sl.bits.p, nbits,
+                           ctx->d_counters, sigma, seed, frame0 + fs);
         ctx->stream = user_stream;
         ctx->frame_base = 0;
-        if (e != cudaSuccess) rc = fail(ctx, MODEM_ERR_CUDA, std::string("loopback pipeline: ") + cudaGetErrorString(e));
+        if (rc) break;
+        e = cudaEventRecord(sl.comp_done, s_k);
+        /* copy out */
+        if (e == cudaSuccess && copies_out) {
+            e = cudaStreamWaitEvent(s_out, sl.comp_done, 0);
+            if (e == cudaSuccess && sym) e = cudaMemcpyAsync(sym + fs * K, sl.sym.p, n * K, cudaMemcpyDeviceToHost, s_out);
+            if (e == cudaSuccess && bits_out)
+                e = cudaMemcpyAsync(bits_out + fs * K * bps, sl.out.p, n * K * bps, cudaMemcpyDeviceToHost, s_out);
+            if (e == cudaSuccess) e = cudaEventRecord(sl.out_done, s_out);
+        }
     }
+    if (e != cudaSuccess && !rc) rc = fail(ctx, MODEM_ERR_CUDA, std::string("loopback pipeline: ") + cudaGetErrorString(e));
     ctx->stream = user_stream;
     ctx->frame_base = 0;
     for (auto& ln : ctx->lanes) {

@@ -253,10 +253,11 @@ cudaError_t tx_rect_fast_launch(const TxArgs& a, cudaStream_t stream)
 
 bool tx_shaped_fast_supported(uint32_t sps, uint32_t n_taps) { return sps == 8 && n_taps == 129; }
 uint64_t tx_shaped_fast_tiles(uint64_t nsym) { return (nsym + kThreads - 1) / kThreads; }
-cudaError_t tx_shaped_fast_launch(const TxArgs& a, const float* h_taps, bool fma, cudaStream_t stream)
+cudaError_t tx_shaped_fast_launch(const TxArgs& a, const float* h_taps, bool fma, bool rail_pairs, cudaStream_t stream)
 {
     dim3 grid((unsigned)tx_shaped_fast_tiles(a.nsym), (unsigned)((a.F + a.frames_per_block - 1) / a.frames_per_block));
-    const TapsParam<129> tp = make_taps_param<129>(h_taps);
+    /* rail_pairs: h_taps holds (h_i[k], h_q[k]) pairs and a.lut holds (+-1, +-1) -- the sign-product form, see modem_api.cu */
+    const TapsParam<129> tp = rail_pairs ? make_taps_param_pairs<129>(h_taps) : make_taps_param<129>(h_taps);
     static const int fb = getenv("MODEM_GPU_TX_FB") ? atoi(getenv("MODEM_GPU_TX_FB")) : 2; /* tuning knob: 2 measured best (exact 3.24 ms, fused 2.58 ms at C3; 4: 3.65 / 2.99) */
     if (fb != 4) {
         if (fma) tx_shaped_fast_kernel<8, 129, true, 2><<<grid, kThreads, 0, stream>>>(a, tp);

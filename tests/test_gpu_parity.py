@@ -93,6 +93,22 @@ def test_tx_shaped_rrc(pkg, orc, force_generic, monkeypatch):
     assert_buffers(tx, tx_ref, "rrc tx")
 
 
+@pytest.mark.parametrize("sign_form", [True, False])
+@pytest.mark.parametrize("scheme", ["qpsk", "bpsk", "bask", "qam16", "16psk"])
+def test_tx_shaped_fast_schemes(pkg, orc, scheme, sign_form, monkeypatch):
+    """Tuned 129-tap / sps 8 shaped TX for constellations with one magnitude per rail (the sign-product
+    form: one exact fma(+-1, round(h*v), acc) per tap instead of multiply + add) and without (plain form);
+    both must be bit-identical to the oracle's multiply-round-add-round fold (fir.rs:21-24)."""
+    if scheme not in MEMORYLESS:
+        pytest.skip(f"{scheme} not a -m scheme name here")
+    if not sign_form:
+        monkeypatch.setenv("MODEM_GPU_NO_SIGN_FORM", "1")
+    kw = path_kwargs(scheme, sps=8, shaped=True)
+    m, o = make(pkg, orc, **kw)
+    bits = rand_bits(23, 5, o.bps * 613)  # ragged against the 256-symbol tile, frames odd against the frame pairs
+    assert_buffers(m.modulate(bits), o.modulate(bits), f"{scheme} shaped tx (sign form {sign_form})")
+
+
 @pytest.mark.parametrize("scheme,sps", [("qam16", 4), ("oqpsk", 10), ("dcqpsk", 5)])
 def test_tx_shaped_generic_schemes(pkg, orc, scheme, sps):
     kw = path_kwargs(scheme, sps=sps, shaped=True)

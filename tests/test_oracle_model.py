@@ -102,3 +102,36 @@ def test_ber_matches_theory(orc):
         _, _, (err, n) = o.loopback(bits, sigma=o.sigma_for_ebn0(db), seed=77, threads=8, want_out=False)
         p = 0.5 * math.erfc(math.sqrt(10 ** (db / 10)))
         assert abs(err / n - p) < 4 * math.sqrt(p / n), (db, err / n, p)
+
+
+def test_shaped_tx_sign_product_form(orc):
+    """The GPU's shaped TX replaces multiply-round-add-round by ONE fma(+-1, round(h[k]*v), acc) when every
+    constellation point is (+-vi, +-vq), and skips the zero-stuffed terms (csrc/modem_api.cu `tx_sign_form`).
+    Model that form in numpy binary32 (a product by +-1 is exact, so `acc + s*p` rounds once, like the fma) and
+    compare it with the oracle's literal fold over all taps (fir.rs:21-24): bit-identical, signed zeros included."""
+    from conftest import path_kwargs
+
+    for scheme in ("qpsk", "bpsk"):
+        kw = path_kwargs(scheme, sps=8, shaped=True)
+        o = orc.OraclePath(**kw)
+        con = o.constellation()[0]
+        v = np.abs(con[0])
+        assert (np.abs(con).view(np.uint32) == v.view(np.uint32)).all(), "one magnitude per rail"
+        sign = np.where(np.signbit(con), F32(-1), F32(1))
+        h = np.asarray(kw["tx_taps"], F32)
+        rail_taps = (h[:, None] * v[None, :]).astype(F32)  # round(h[k] * v), one rounding
+        bits = np.random.default_rng(5).integers(0, 2, (1, o.bps * 90), dtype=np.uint8)
+        _, iq_ref = o.modulate(bits, want_iq=True)
+        nsym = bits.shape[1] // o.bps
+        sym = np.zeros(nsym, np.int64)
+        for b in range(o.bps):
+            sym = (sym << 1) | bits[0, b::o.bps][:nsym]
+        s = sign[sym]  # [nsym][2]
+        sps, L = 8, nsym * 8
+        acc = np.zeros((L, 2), F32)
+        n = np.arange(L)
+        for k in range(len(h)):  # ascending taps; only n-k on a symbol instant contributes
+            m = n - k
+            hit = (m >= 0) & (m % sps == 0)
+            acc[hit] = acc[hit] + s[m[hit] // sps] * rail_taps[k]
+        assert (acc.view(np.uint32) == iq_ref[0].view(np.uint32)).all()
