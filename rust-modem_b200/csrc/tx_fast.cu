@@ -4,6 +4,7 @@
  */
 #include <stdlib.h>
 
+#include <type_traits>
 #include "launch.h"
 
 namespace mg {
@@ -117,7 +118,7 @@ __global__ void __launch_bounds__(kThreads, 4) tx_rect_fast_kernel(const __grid_
  * accumulator still sees its taps in ascending order (fir.rs:21-24; the zero-stuffed terms are exact no-ops).
  * The CTA's 2 KB-per-warp output is transposed through shared memory so global stores are 128-bit coalesced.
  */
-template <int SPS, int NT, bool FMA, int FB>
+template <int SPS, int NT, bool FMA, int FB, int BPSW>
 __global__ void __launch_bounds__(kThreads, FB >= 4 ? 2 : 3)
     tx_shaped_fast_kernel(const __grid_constant__ TxArgs a, const __grid_constant__ TapsParam<NT> taps)
 {
@@ -152,27 +153,75 @@ __global__ void __launch_bounds__(kThreads, FB >= 4 ? 2 : 3)
         for (int p = 0; p < SPS; ++p) mg_sincosf(nco_phase(w, a.sample0 + m * SPS + p), &sn[p], &cs[p]);
     }
 
-    /* mapped symbols of FB frames: s_sym[buf][g][i] = (i, q) of symbol k0 - HALO + i of frame fg + g */
-    auto stage = [&](int buf, u64 fg) {
-        for (int i = tid; i < ROW; i += kThreads) {
-            const long long mm = (long long)k0 - HALO + i;
-            const bool in = mm >= 0 && (u64)mm < a.nsym;
-            const uint32_t toff = in ? (uint32_t)((u64)mm % a.n_tables) * a.n_const : 0u;
+    /* mapped symbols of FB frames: s_sym[buf][g][i] = (i, q) of symbol k0 - HALO + i of frame fg + g.  A thread
+     * stages row entry `tid` (and, the first HALO threads, entry kThreads + tid); which symbols those are, whether
+     * they exist and which table they use does not depend on the frame.  The fetch of the NEXT group's bits is
+     * issued before the FIR of the current one and only consumed (table lookup, shared store) after it: in the
+     * first form the lookup directly behind the load stalled every warp on the global latency, then on the
+     * barrier (ncu: 30 % + 27 % of the stall samples, profiles/r01_c3_signform_ncu.txt). */
+    const uint32_t bps = a.bps;
+    /* BPSW > 0: a symbol's BPSW bytes are one aligned word (checked by the launcher); 0: byte-wise fallback */
+    constexpr bool word = BPSW > 0;
+    using raw_t = typename std::conditional<BPSW == 8, unsigned long long, uint32_t>::type;
+    bool in_e[2];
+    uint32_t toff_e[2];
+    const uint8_t* src_e[2];
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+        const long long mm = (long long)k0 - HALO + tid + e * kThreads;
+        in_e[e] = (e == 0 || tid < HALO) && mm >= 0 && (u64)mm < a.nsym;
+        toff_e[e] = (in_e[e] && a.n_tables > 1) ? (uint32_t)((u64)mm % a.n_tables) * a.n_const : 0u;
+        src_e[e] = a.bits + (in_e[e] ? (u64)mm * bps : 0);
+    }
+    raw_t raw[2][FB]; /* the symbols' bytes as loaded (word) or already packed (byte-wise fallback) */
+    auto fetch = [&](u64 fg) {
+#pragma unroll
+        for (int e = 0; e < 2; ++e)
+#pragma unroll
+            for (int g = 0; g < FB; ++g) {
+                raw_t r = 0;
+                if (in_e[e] && fg + g < f1) {
+                    const uint8_t* p = src_e[e] + (fg + g) * a.nbits;
+                    if (BPSW == 0) r = pack_symbol(p, bps);
+                    else if (BPSW == 1) r = __ldg(p);
+                    else if (BPSW == 2) r = __ldg(reinterpret_cast<const uint16_t*>(p));
+                    else if (BPSW == 4) r = __ldg(reinterpret_cast<const uint32_t*>(p));
+                    else r = (raw_t)__ldg(reinterpret_cast<const unsigned long long*>(p));
+                }
+                raw[e][g] = r;
+            }
+    };
+    auto commit = [&](int buf, u64 fg) {
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            if (e == 1 && tid >= HALO) break;
 #pragma unroll
             for (int g = 0; g < FB; ++g) {
                 float2 v = make_float2(0.0f, 0.0f);
-                if (in && fg + g < f1) v = s_lut[toff + sym_index_plain(a.bits + (fg + g) * a.nbits, (u64)mm, a.bps)];
-                s_sym[buf][g][i] = v;
+                if (in_e[e] && fg + g < f1) {
+                    uint32_t idx = (uint32_t)raw[e][g];
+                    if (word) { /* digital/util.rs:5-11: first byte is the MSB */
+                        idx = 0;
+#pragma unroll
+                        for (int j = 0; j < BPSW; ++j) idx = (idx << 1) | ((uint32_t)(raw[e][g] >> (8 * j)) & 1u);
+                    }
+                    v = s_lut[toff_e[e] + idx];
+                }
+                s_sym[buf][g][tid + e * kThreads] = v;
             }
         }
     };
     __syncthreads();
-    if (f0 < f1) stage(0, f0);
+    if (f0 < f1) {
+        fetch(f0);
+        commit(0, f0);
+    }
     __syncthreads();
 
     int buf = 0;
     for (u64 fg = f0; fg < f1; fg += FB, buf ^= 1) {
-        if (fg + FB < f1) stage(buf ^ 1, fg + FB); /* overlap the next group's symbol fetch */
+        const bool more = fg + FB < f1;
+        if (more) fetch(fg + FB); /* in flight during the FIR */
         f32x2 acc[FB][SPS];
 #pragma unroll
         for (int g = 0; g < FB; ++g)
@@ -220,6 +269,7 @@ __global__ void __launch_bounds__(kThreads, FB >= 4 ? 2 : 3)
                 __syncwarp();
             }
         }
+        if (more) commit(buf ^ 1, fg + FB);
         __syncthreads(); /* s_sym[buf^1] staged, s_sym[buf] free for the group after next */
     }
 }
@@ -258,14 +308,23 @@ cudaError_t tx_shaped_fast_launch(const TxArgs& a, const float* h_taps, bool fma
     dim3 grid((unsigned)tx_shaped_fast_tiles(a.nsym), (unsigned)((a.F + a.frames_per_block - 1) / a.frames_per_block));
     /* rail_pairs: h_taps holds (h_i[k], h_q[k]) pairs and a.lut holds (+-1, +-1) -- the sign-product form, see modem_api.cu */
     const TapsParam<129> tp = rail_pairs ? make_taps_param_pairs<129>(h_taps) : make_taps_param<129>(h_taps);
-    static const int fb = getenv("MODEM_GPU_TX_FB") ? atoi(getenv("MODEM_GPU_TX_FB")) : 2; /* tuning knob: 2 measured best (exact 3.24 ms, fused 2.58 ms at C3; 4: 3.65 / 2.99) */
-    if (fb != 4) {
-        if (fma) tx_shaped_fast_kernel<8, 129, true, 2><<<grid, kThreads, 0, stream>>>(a, tp);
-        else tx_shaped_fast_kernel<8, 129, false, 2><<<grid, kThreads, 0, stream>>>(a, tp);
-    } else {
-        if (fma) tx_shaped_fast_kernel<8, 129, true, 4><<<grid, kThreads, 0, stream>>>(a, tp);
-        else tx_shaped_fast_kernel<8, 129, false, 4><<<grid, kThreads, 0, stream>>>(a, tp);
+    /* two frames per tap fetch: measured best (four: exact 3.65 ms against 3.24 ms at C3, fused 2.99 against 2.58) */
+    const uint32_t bps = a.bps;
+    const bool word = (bps == 1 || bps == 2 || bps == 4 || bps == 8) && (a.nbits % bps == 0) &&
+                      ((reinterpret_cast<uintptr_t>(a.bits) % bps) == 0);
+#define MG_TXS(W)                                                                              \
+    do {                                                                                       \
+        if (fma) tx_shaped_fast_kernel<8, 129, true, 2, W><<<grid, kThreads, 0, stream>>>(a, tp);  \
+        else tx_shaped_fast_kernel<8, 129, false, 2, W><<<grid, kThreads, 0, stream>>>(a, tp);     \
+    } while (0)
+    switch (word ? bps : 0u) {
+    case 1: MG_TXS(1); break;
+    case 2: MG_TXS(2); break;
+    case 4: MG_TXS(4); break;
+    case 8: MG_TXS(8); break;
+    default: MG_TXS(0); break;
     }
+#undef MG_TXS
     return cudaGetLastError();
 }
 
