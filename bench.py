@@ -195,8 +195,9 @@ def main():
     d_cnt = torch.zeros(2, dtype=torch.int64, device="cuda")
 
     def step():
-        """one pass of the hot path: the loopback (TX kernels || RX kernels, chunk-pipelined on two
-        streams by the library) + the tiny all-reduce of the counters"""
+        """one pass of the hot path: the device-resident loopback (for this workload ONE fused kernel that makes the
+        TX samples, stores them and demodulates them; two kernels when MODEM_GPU_NO_FUSED_LOOP=1) + the tiny
+        all-reduce of the counters"""
         d_cnt.zero_()
         m.loopback_device_into(d_bits, F, NBITS, d_cnt, tx=d_tx, sym=d_sym, bits_out=d_out)
         if comm is not None:
@@ -245,6 +246,15 @@ def main():
     sync_all()
     tx_ms = float(np.mean([e[0].elapsed_time(e[1]) for e in evs[3:]]))
     rx_ms = float(np.mean([e[1].elapsed_time(e[2]) for e in evs[3:]]))
+    # the loopback entry alone (no counter reset, no all-reduce): the fused kernel's launch duration when it is one launch
+    fused = launches == args.steps
+    lev = [[torch.cuda.Event(enable_timing=True) for _ in range(2)] for _ in range(3 + args.steps)]
+    for e in lev:
+        e[0].record(stream)
+        m.loopback_device_into(d_bits, F, NBITS, d_cnt, tx=d_tx, sym=d_sym, bits_out=d_out)
+        e[1].record(stream)
+    sync_all()
+    loop_ms = float(np.mean([e[0].elapsed_time(e[1]) for e in lev[3:]]))
     clocks = sampler.stop() if rank == 0 else None
 
     tt = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
@@ -282,6 +292,11 @@ def main():
         rx_bps = 8 + (1 + BPS) / SPS + BPS / SPS
         kern = {"tx_rect_kernel": (tx_ms, tx_bps), "rx_fast_kernel": (rx_ms, rx_bps)}
         dom = max(kern, key=lambda k: kern[k][0])
+        if fused:
+            # one kernel: writes the 8 B sample, reads bps/sps B of bits (once: they are also the reference bits of the
+            # error count) and writes (1 + bps)/sps B of symbols + bits -- SURVEY.md 8(d)'s fused figure
+            kern["loop_fused_kernel"] = (loop_ms, 8 + BPS / SPS + (1 + BPS) / SPS)
+            dom = "loop_fused_kernel"
         traffic = {}
         tp = os.path.join(ROOT, "profiles", "traffic.json")  # dram__bytes_read+write per launch, from the committed ncu capture
         if os.path.exists(tp):
@@ -292,10 +307,14 @@ def main():
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "frames_per_gpu": F, "samples_per_frame": L,
-                       "l2": "per step 2 GiB of TX samples are written and read per GPU (16x the 126 MB L2), no flush "
-                             "between steps: every step's inputs are far larger than L2; a step is one whole-buffer TX launch and one "
-                             "whole-buffer RX launch (the library's chunked TX||RX pipeline is off by default, DESIGN.md 4); "
-                             "roofline.kernels are the same two launches timed separately",
+                       "l2": ("per step 2 GiB of TX samples are written per GPU (16x the 126 MB L2), no flush between steps: "
+                              "every step's buffers are far larger than L2; a step is ONE launch of the fused loopback kernel "
+                              "(rx_fast_kernel<..., TXF>: makes the TX samples from the bits, stores them, demodulates them from "
+                              "registers; DESIGN.md 4); roofline.kernel is that launch timed alone; roofline.kernels also lists the "
+                              "two kernels of the unfused path (modulate, then demodulate from memory) for comparison") if fused else
+                             ("per step 2 GiB of TX samples are written and read per GPU (16x the 126 MB L2), no flush "
+                              "between steps: every step's inputs are far larger than L2; a step is one whole-buffer TX launch and one "
+                              "whole-buffer RX launch; roofline.kernels are the same two launches timed separately"),
                        "parallelism": f"frames sharded over {world} GPU(s), one NCCL all-reduce of 2 u64 counters"},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": ach[dom], "peak": peak, "unit": "GB/s",

@@ -104,6 +104,7 @@ struct modem_ctx {
     bool use_graph = true; /* MODEM_GPU_NO_GRAPH=1 disables */
     uint64_t launches = 0;
     bool force_generic = false;
+    bool no_fused_loop = false; /* MODEM_GPU_NO_FUSED_LOOP=1: the loopback entries run the TX and the RX kernel separately */
     int rx_variant = 0; /* MODEM_GPU_RX_VARIANT: tuning knob, 0 = default */
     int rx_fpb = 0, rx_tile_major = -1; /* MODEM_GPU_RX_FPB / MODEM_GPU_RX_TILEMAJOR: tuning knobs */
     size_t pipe_chunk = 0; /* MODEM_GPU_PIPE_CHUNK: frames per pipeline chunk (0 = ~64 MB of TX samples) */
@@ -512,6 +513,69 @@ int launch_rx(modem_ctx* ctx, const float2* d_rx, u64 F, u64 L, uint8_t* d_sym, 
 
 
 /* ------------------------------------------------------------------ stateful phasors (TX) */
+/*
+ * Fused loopback: one kernel makes the TX samples of a tile from the bits, stores them (the TX buffer the caller
+ * gets is the same, bit for bit) and demodulates them from registers -- the RX side's 8 B/sample read is gone.
+ * Eligible: the headline shape (QPSK table, rectangular hold, sps 8, the 64-tap low-pass, odd decision delay, exact
+ * MACs, no noise, no phase offset anywhere so that both sides share one NCO table).  Returns 1 = launched,
+ * 0 = not eligible (the caller runs the two kernels), < 0 = error.
+ */
+/* the shape test of the fused loopback; fills the geometry of `a`.  d_tx may be null: the samples are then not stored
+ * at all (a caller that did not ask for the TX buffer gets a loopback without any sample traffic) */
+bool loop_fused_eligible(modem_ctx* ctx, const uint8_t* d_bits, u64 F, u64 nbits, const float2* d_tx, float sigma, mg::RxArgs& a)
+{
+    const modem_cfg_t& c = ctx->cfg;
+    if (ctx->no_fused_loop || ctx->force_generic || ctx->phasor_on || ctx->rx_variant || sigma != 0.0f) return false;
+    if (c.n_tx_taps || c.bits_per_symbol != 2 || c.n_tables != 1 || c.q_offset || c.samples_per_symbol != 8 || c.n_rx_taps != 64 ||
+        (c.flags & MODEM_FLAG_FUSED_MAC) || !ctx->cs_rx_shared)
+        return false;
+    if (!d_bits || (nbits & 1u) || (reinterpret_cast<uintptr_t>(d_bits) & 1u) || (d_tx && !aligned16(d_tx))) return false;
+    a.L = (nbits / 2) * 8;
+    a.F = F;
+    a.K = modem_gpu_decided_symbols(ctx, a.L);
+    if (F == 0 || a.L == 0 || a.K == 0 || a.L >= (1ull << 32)) return false;
+    a.delay = c.decision_delay;
+    return mg::loop_fused_supported_64(a);
+}
+
+int launch_loop_fused(modem_ctx* ctx, const uint8_t* d_bits, u64 F, u64 nbits, float2* d_tx, uint8_t* d_sym, uint8_t* d_out,
+                      u64* d_counters, float sigma)
+{
+    const modem_cfg_t& c = ctx->cfg;
+    mg::RxArgs a{};
+    if (!d_counters || !loop_fused_eligible(ctx, d_bits, F, nbits, d_tx, sigma, a)) return 0;
+    a.sym = d_sym;
+    a.bits = d_out;
+    a.ref_bits = d_bits;
+    a.ref_stride = nbits;
+    a.counters = d_counters;
+    a.slut = ctx->d_slut;
+    a.bps = 2;
+    a.sps = 8;
+    a.n_tables = 1;
+    a.n_const = 4;
+    a.delay = c.decision_delay;
+    a.rx_gain = c.rx_gain;
+    a.ch = channel_view(ctx);
+    a.sample0 = c.sample0;
+    a.taps = ctx->d_rx_taps;
+    a.n_taps = 64;
+    a.tx_out = d_tx;
+    for (int j = 0; j < 4; ++j) a.tx_iq[j] = make_float2(ctx->h_const[2 * j], ctx->h_const[2 * j + 1]);
+    const u64 tiles = (a.K + mg::loop_fused_tile_symbols_64() - 1) / mg::loop_fused_tile_symbols_64();
+    a.frames_per_block = std::min<uint32_t>(frames_per_block(ctx, F, tiles), 16);
+    if (ctx->rx_fpb > 0 && !ctx->n_channels) a.frames_per_block = (uint32_t)std::max<u64>(ctx->rx_fpb, (F + 65534) / 65535);
+    if (ctx->n_channels) while (ctx->frames_per_channel % a.frames_per_block || ctx->frame_base % a.frames_per_block) --a.frames_per_block;
+    a.tile_major = ctx->rx_tile_major == 0 ? 0u : 1u;
+    int rc = attach_carrier_table(ctx, a.ch, F, a.L, true);
+    if (rc) return rc;
+    if (!a.ch.cs_tab) return 0;
+    cudaError_t e = mg::loop_fused_launch_64(a, ctx->h_rx_taps.data(), ctx->stream);
+    if (e != cudaSuccess) return fail(ctx, MODEM_ERR_CUDA, std::string("fused loopback: ") + cudaGetErrorString(e));
+    ctx->launches++;
+    return 1;
+}
+
 int launch_tx_phasor(modem_ctx* ctx, mg::TxArgs& a)
 {
     const modem_phasor_t& ph = ctx->phasor;
@@ -752,6 +816,8 @@ int modem_gpu_create(modem_ctx_t** out, int device, const modem_cfg_t* cfg)
     ctx->cfg.tx_taps = cfg->n_tx_taps ? ctx->h_tx_taps.data() : nullptr;
     const char* fg = getenv("MODEM_GPU_FORCE_GENERIC");
     ctx->force_generic = fg && fg[0] == '1';
+    const char* nf = getenv("MODEM_GPU_NO_FUSED_LOOP");
+    ctx->no_fused_loop = nf && nf[0] == '1';
     const char* rv = getenv("MODEM_GPU_RX_VARIANT");
     ctx->rx_variant = rv ? atoi(rv) : 0;
     const char* rf = getenv("MODEM_GPU_RX_FPB");
@@ -1180,6 +1246,9 @@ int loopback_pipelined(modem_ctx* ctx, const uint8_t* bits, size_t F, size_t nbi
         if (e != cudaSuccess) break;
         ctx->stream = s_k; /* launch_* enqueue on ctx->stream */
         ctx->frame_base = fs;
+        /* two kernels per chunk here: the fused loopback kernel (launch_loop_fused) measured SLOWER in this pipeline
+         * (2.1 ms against 1.65 ms per step, with or without storing the samples) whenever the copy-out of the previous
+         * chunk runs beside it; with the copy-out off both forms take 1.37 ms (tools/gpu_e2e_probe2.py) */
         rc = launch_tx(ctx, (const uint8_t*)sl.bits.p, n, nbits, (float2*)ctx->pipe_tx.p, nullptr);
         if (!rc)
             rc = launch_rx(ctx, (const float2*)ctx->pipe_tx.p, n, L, sym ? (uint8_t*)sl.sym.p : nullptr,
@@ -1261,7 +1330,8 @@ int modem_gpu_loopback_device(modem_ctx_t* ctx, const uint8_t* bits, size_t F, s
     const size_t bps = ctx->cfg.bits_per_symbol;
     if (F == 0 || L == 0) return MODEM_OK;
     float2* d_tx = (float2*)tx;
-    if (!d_tx) {
+    mg::RxArgs probe{};
+    if (!d_tx && !loop_fused_eligible(ctx, bits, F, nbits, nullptr, sigma, probe)) { /* the fused kernel needs no sample buffer */
         int rc = ensure(ctx, ctx->s_tx, F * L * sizeof(float2));
         if (rc) return rc;
         d_tx = (float2*)ctx->s_tx.p;
@@ -1302,6 +1372,18 @@ int modem_gpu_loopback_device(modem_ctx_t* ctx, const uint8_t* bits, size_t F, s
         for (size_t fs = 0; fs < F && !rc && e == cudaSuccess; fs += Fc, ++c) {
             const size_t n = std::min(Fc, F - fs);
             ctx->frame_base = fs;
+            /* the headline shape runs as ONE kernel (TX samples made, stored and demodulated in place) */
+            rc = launch_loop_fused(ctx, bits + fs * nbits, n, nbits, d_tx ? d_tx + fs * L : nullptr, sym ? sym + fs * K : nullptr,
+                                   bits_out ? bits_out + fs * K * bps : nullptr, (u64*)counters, sigma);
+            if (rc == 1) {
+                rc = MODEM_OK;
+                continue;
+            }
+            if (rc) break;
+            if (!d_tx) {
+                rc = fail(ctx, MODEM_ERR_INVALID, "loopback_device: internal: no sample buffer for the two-kernel path");
+                break;
+            }
             rc = launch_tx(ctx, bits + fs * nbits, n, nbits, d_tx + fs * L, nullptr); /* on the user stream */
             if (rc) break;
             cudaEvent_t ev = ctx->ev_pool[c % 8];

@@ -165,7 +165,7 @@ __device__ __forceinline__ uint32_t slice_point_reg4(const float2 (&t)[4], float
     return best;
 }
 
-template <int NT, int OFF, bool FMA, bool NOISE, int THREADS, int MINB, int R, int PF, int TMC>
+template <int NT, int OFF, bool FMA, bool NOISE, int THREADS, int MINB, int R, int PF, int TMC, bool TXF = false>
 __global__ void __launch_bounds__(THREADS, MINB)
     rx_fast_kernel(const __grid_constant__ RxArgs a, const __grid_constant__ TapsParam<NT> taps)
 {
@@ -259,11 +259,35 @@ __global__ void __launch_bounds__(THREADS, MINB)
             xr[it][1] = t.z;
         }
     };
-    if (PF == 2 && f0 < f1) load_tile(frame);
+    /* ---- TXF: the fused loopback.  The tile's TX samples are not read from memory but MADE here, from the frame's
+     * bits (a.ref_bits, two bytes per QPSK symbol) with the arithmetic of the rectangular-hold TX kernel
+     * (data.rs:66-79 hold, qpsk.rs:23-35 table, modulator.rs:37-48 mix: re = i*cos - q*sin, im = i*sin + q*cos, each
+     * operation rounded on its own), stored to a.tx_out exactly once (a tile owns the samples behind its halo; the
+     * first tile also owns the frame's head) and fed to the demodulator from registers: the 8 B/sample read of the
+     * RX side disappears, the loopback is one pass of 8 B/sample written + bits.  Same NCO values on both sides
+     * (no phase offset: the launcher checks), so every buffer is bit-identical to the two-kernel path. */
+    uint32_t sw[TXF ? C::ITER : 1]; /* the symbol's two bit bytes, per staged chunk */
+    const bool first_tile = k0 == 0;
+    static_assert(!TXF || THREADS == 64, "symbol stride per step = 2*THREADS/8");
+    /* -> the two bit bytes of this thread's first chunk: symbol (nbase + 2*tid) >> 3; chunk it*THREADS + tid: 16 symbols on per
+     * step.  (Staging the tile's ~0.5 KB of bits through shared memory by cp.async, one frame ahead, measured 6 % slower
+     * than these direct loads: 0.692 against 0.654 ms at C2.) */
+    const uint8_t* brow = TXF ? a.ref_bits + f0 * a.ref_stride + 2 * ((nbase + 2 * (long long)tid) >> 3) : nullptr;
+    float4* txrow = TXF ? reinterpret_cast<float4*>(a.tx_out + f0 * a.L + nbase) + tid : nullptr;
+    auto load_syms = [&]() {
+#pragma unroll
+        for (int it = 0; it < C::ITER; ++it) {
+            uint32_t w = 0;
+            if ((vmask >> it) & 1ull) w = __ldg(reinterpret_cast<const uint16_t*>(brow + 32 * it));
+            sw[TXF ? it : 0] = w;
+        }
+    };
+    if (PF == 2 && f0 < f1 && !TXF) load_tile(frame);
     for (u64 f = f0; f < f1; ++f, orow += a.K, frame += a.L) {
         __syncthreads(); /* previous frame's phase B finished; s_slut visible */
         /* ---- phase A: load the tile (all loads issued before the first use), mix, stage */
-        if (PF != 2) load_tile(frame);
+        if (TXF) load_syms();
+        else if (PF != 2) load_tile(frame);
         if (NOISE) {
             /* G chunks per trip: their Philox / logf / sqrt / sincos chains are independent, so the scheduler can
              * interleave them (one chunk per trip left ~2 independent chains per warp at 4 warps per scheduler:
@@ -301,6 +325,19 @@ __global__ void __launch_bounds__(THREADS, MINB)
             if (it * THREADS + tid < C::NCHUNK) {
                 const float4 cs = (TMC > 0 && it < TCH) ? make_float4(parked[(4 * it) % (TMC > 0 ? TMC : 4)], parked[(4 * it + 1) % (TMC > 0 ? TMC : 4)], parked[(4 * it + 2) % (TMC > 0 ? TMC : 4)], parked[(4 * it + 3) % (TMC > 0 ? TMC : 4)])
                                                         : LDC(cs4 + it * THREADS);
+                if (TXF) {
+                    const uint32_t w = sw[TXF ? it : 0];
+                    const bool b0 = (w & 1u) != 0, b1 = (w & 0x100u) != 0; /* first byte = MSB (digital/util.rs:5-11) */
+                    const float si = b0 ? (b1 ? a.tx_iq[3].x : a.tx_iq[2].x) : (b1 ? a.tx_iq[1].x : a.tx_iq[0].x);
+                    const float sq = b0 ? (b1 ? a.tx_iq[3].y : a.tx_iq[2].y) : (b1 ? a.tx_iq[1].y : a.tx_iq[0].y);
+                    const float2 x0 = mix_iq(si, sq, cs.x, cs.y), x1 = mix_iq(si, sq, cs.z, cs.w);
+                    const bool live = ((vmask >> it) & 1ull) != 0;
+                    /* this tile owns local samples >= 8*(NB-1) (what the previous tile did not reach) */
+                    const bool own = first_tile || it > 0 || tid >= 4 * (C::NB - 1);
+                    if (live && own && a.tx_out) __stcs(txrow + it * THREADS, make_float4(x0.x, x0.y, x1.x, x1.y));
+                    xr[it][0] = live ? x0.x : 0.0f;
+                    xr[it][1] = live ? x1.x : 0.0f;
+                }
                 /* demodulator.rs:53-54: x*cos, x*(-sin); chunk q = it*THREADS + tid sits at position
                  * q + q/PADW = wbase + it*(THREADS + THREADS/PADW) */
                 s_v[wbase + it * (THREADS + THREADS / C::PADW)] =
@@ -309,15 +346,26 @@ __global__ void __launch_bounds__(THREADS, MINB)
             }
         }
         __syncthreads();
-        if (PF == 2 && f + 1 < f1) load_tile(frame + a.L); /* next frame's loads fly during the FIR */
+        if (TXF) {
+            brow += a.ref_stride;
+            txrow += a.L / 2;
+            /* the next frame's bits of this tile (2 B per symbol, ~0.5 KB) towards L2 while the FIR runs */
+            if (f + 1 < f1 && tid < (2 * C::NBLK + 127) / 128 + 1) {
+                const uint8_t* row = a.ref_bits + (f + 1) * a.ref_stride;
+                long long o = 2 * (nbase >> 3) + 128 * (long long)tid;
+                o = o < 0 ? 0 : (o >= (long long)a.ref_stride ? (long long)a.ref_stride - 1 : o);
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(row + o));
+            }
+        }
+        if (PF == 2 && f + 1 < f1 && !TXF) load_tile(frame + a.L); /* next frame's loads fly during the FIR */
         /* pull the next frame's tile towards L2 while the FIR runs: PF 1 = one prefetch per 128-byte
          * line through the LSU, PF 3 = one bulk (TMA) L2 prefetch of the whole tile by one thread */
-        if (PF == 1 && f + 1 < f1) {
+        if (PF == 1 && f + 1 < f1 && !TXF) {
             const char* nxt = reinterpret_cast<const char*>(frame + a.L + vlo_n);
             for (int o = tid * 128; o < (int)(vhi_n - vlo_n) * 8; o += THREADS * 128)
                 asm volatile("prefetch.global.L2 [%0];" ::"l"(nxt + o));
         }
-        if (PF == 3 && f + 1 < f1 && tid == 0 && vhi_n > vlo_n) {
+        if (PF == 3 && !TXF && f + 1 < f1 && tid == 0 && vhi_n > vlo_n) {
             const char* nxt = reinterpret_cast<const char*>(frame + a.L + vlo_n);
             asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(nxt), "r"((int)(vhi_n - vlo_n) * 8) : "memory");
         }
@@ -456,7 +504,7 @@ __global__ void __launch_bounds__(THREADS, MINB)
 }
 
 /* ------------------------------------------------------------------ host side */
-template <int NT, int OFF, bool FMA, bool NOISE, int THREADS, int MINB, int R, int PF = RX_DEFAULT_PF, int TMC = RX_DEFAULT_TMC>
+template <int NT, int OFF, bool FMA, bool NOISE, int THREADS, int MINB, int R, int PF = RX_DEFAULT_PF, int TMC = RX_DEFAULT_TMC, bool TXF = false>
 cudaError_t rx_fast_launch_t(const RxArgs& a, const float* h_taps, cudaStream_t stream)
 {
     using C = RxFastCfg<NT, OFF, THREADS, R>;
@@ -464,7 +512,7 @@ cudaError_t rx_fast_launch_t(const RxArgs& a, const float* h_taps, cudaStream_t 
     dim3 grid = a.tile_major ? dim3(groups, tiles) : dim3(tiles, groups);
     const TapsParam<NT> tp = make_taps_param<NT>(h_taps);
     const size_t smem = C::smem(a.n_tables * a.n_const);
-    auto kern = rx_fast_kernel<NT, OFF, FMA, NOISE, THREADS, MINB, R, PF, TMC>;
+    auto kern = rx_fast_kernel<NT, OFF, FMA, NOISE, THREADS, MINB, R, PF, TMC, TXF>;
     static size_t configured = 0; /* per instantiation: set the attributes once per shared-memory size */
     if (configured != smem) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -158,9 +158,11 @@ def test_hot_kernels_do_not_spill(pkg):
     """The tuned RX kernel sits at its register cap (128 at 8 CTAs/SM): an innocent change to the argument structs
     once cost 8 bytes of spill and 7 % of its speed.  The ptxas log of the in-tree build is the guard."""
     logdir = os.path.join(ROOT, "rust-modem_b200", "lib")
-    hot = {"rx_fast_64.ptxas.log": "_ZN2mg14rx_fast_kernelILi64ELi0ELb0ELb0ELi64ELi8ELi4ELi3ELi64EEE",
-           "tx_fast.ptxas.log": "_ZN2mg19tx_rect_fast_kernelILi2ELb0ELb0EEE"}
-    for fn, sym in hot.items():
+    hot = [("rx_fast_64.ptxas.log", "_ZN2mg14rx_fast_kernelILi64ELi0ELb0ELb0ELi64ELi8ELi4ELi3ELi64ELb0EEE"),
+           ("loop_fused_64.ptxas.log", "_ZN2mg14rx_fast_kernelILi64ELi0ELb0ELb0ELi64ELi8ELi4ELi3ELi64ELb1EEE"),  # the fused loopback
+           ("tx_fast.ptxas.log", "_ZN2mg19tx_rect_fast_kernelILi2ELb0ELb0EEE"),
+           ("tx_fast.ptxas.log", "_ZN2mg21tx_shaped_fast_kernelILi8ELi129ELb1ELi2ELi2EEE")]  # C3 TX, sign-product form
+    for fn, sym in hot:
         path = os.path.join(logdir, fn)
         if not os.path.exists(path):
             pytest.skip("library was not built here")

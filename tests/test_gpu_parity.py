@@ -450,3 +450,94 @@ def test_full_size_c2_properties(pkg, orc):
     assert_buffers(d_tx[idx].cpu().numpy(), tx_ref, "C2 sampled tx")
     _, sym_ref, _ = o.demodulate(tx_ref, want_filt=False)
     assert np.array_equal(d_sym[idx].cpu().numpy(), sym_ref)
+
+
+# ----------------------------------------------------------------------------- fused loopback kernel
+def _device_loopback(pkg, m, bits, want_sym=True, want_bits=True, want_tx=True):
+    import torch
+
+    m.set_stream(torch.cuda.current_stream().cuda_stream)
+    F, nbits = bits.shape
+    L = m.frame_samples(nbits)
+    K = m.decided_symbols(L)
+    d_bits = torch.from_numpy(bits).cuda()
+    d_tx = torch.full((F, L, 2), float("nan"), dtype=torch.float32, device="cuda") if want_tx else None  # every sample must be written
+    d_sym = torch.full((F, K), 255, dtype=torch.uint8, device="cuda") if want_sym else None
+    d_out = torch.full((F, 2 * K), 255, dtype=torch.uint8, device="cuda") if want_bits else None
+    d_cnt = torch.zeros(2, dtype=torch.int64, device="cuda")
+    n0 = m.launch_count
+    m.loopback_device_into(d_bits, F, nbits, d_cnt, tx=d_tx, sym=d_sym, bits_out=d_out)
+    torch.cuda.synchronize()
+    return (None if d_tx is None else d_tx.cpu().numpy(), None if d_sym is None else d_sym.cpu().numpy(), None if d_out is None else d_out.cpu().numpy(),
+            tuple(d_cnt.tolist()), m.launch_count - n0)
+
+
+@pytest.mark.parametrize("F,nsym", [(1, 8), (16, 2048), (6, 1064), (19, 8 * 37), (3, 300), (21, 1111), (40, 2048 + 5), (9, 256 * 3 + 251), (5, 256 * 2 + 4)])
+def test_fused_loopback_matches_oracle_and_two_kernel_path(pkg, orc, F, nsym, monkeypatch):
+    """The fused loopback kernel (TX samples made, stored and demodulated by one kernel) against the oracle and
+    against the two-kernel path: TX buffer bit-identical and completely written (ragged tiles, frames that end inside
+    a tile's halo, frame counts that do not fill a CTA's frame group), symbols, bits and counters equal.  Shapes whose
+    tiles do not reach the frame's end fall back to two kernels (last case): same results, two launches."""
+    kw = path_kwargs("qpsk", sps=8)
+    bits = rand_bits(200 + F, F, 2 * nsym)
+    m, o = make(pkg, orc, **kw)
+    tx_ref = o.modulate(bits)
+    sym_ref, bits_ref, cnt_ref = o.loopback(bits, threads=4)
+    tx, sym, out, cnt, launches = _device_loopback(pkg, m, bits)
+    assert_buffers(tx, tx_ref, "fused tx")
+    assert np.array_equal(sym, sym_ref) and np.array_equal(out, bits_ref)
+    assert cnt == (cnt_ref[0], cnt_ref[1]) and cnt[0] == 0
+    monkeypatch.setenv("MODEM_GPU_NO_FUSED_LOOP", "1")
+    m2 = pkg.Modem(**kw)
+    tx2, sym2, out2, cnt2, launches2 = _device_loopback(pkg, m2, bits)
+    assert np.array_equal(tx.view(np.uint32), tx2.view(np.uint32))
+    assert np.array_equal(sym, sym2) and np.array_equal(out, out2) and cnt == cnt2
+    fallback = nsym % 256 == 4  # K = nsym - 4 fills its tiles exactly: the last tile stops 4 samples short of the frame's end
+    assert launches2 == 3 and launches == (3 if fallback else 2), (launches, launches2)  # NCO table + kernels
+
+
+def test_fused_loopback_is_one_kernel_and_optional_outputs(pkg, orc):
+    """Headline shape: exactly one kernel besides the NCO table; outputs may be left out."""
+    kw = path_kwargs("qpsk", sps=8)
+    bits = rand_bits(77, 33, 2 * 1024)
+    m, o = make(pkg, orc, **kw)
+    _device_loopback(pkg, m, bits)  # first call also builds the NCO table
+    tx, sym, out, cnt, launches = _device_loopback(pkg, m, bits)
+    assert launches == 1, launches
+    tx_ref = o.modulate(bits)
+    assert_buffers(tx, tx_ref, "fused tx")
+    tx3, sym3, out3, cnt3, _ = _device_loopback(pkg, m, bits, want_sym=False, want_bits=False)
+    assert sym3 is None and out3 is None and cnt3 == cnt
+    assert np.array_equal(tx3.view(np.uint32), tx_ref.view(np.uint32))
+    # no TX buffer asked for: the samples never leave the chip, the decisions are the same
+    tx4, sym4, out4, cnt4, launches4 = _device_loopback(pkg, m, bits, want_tx=False)
+    assert tx4 is None and launches4 == 1 and np.array_equal(sym4, sym) and np.array_equal(out4, out) and cnt4 == cnt
+
+
+def test_fused_loopback_bank_and_fallbacks(pkg, orc):
+    """A carrier bank (one NCO table row per channel) runs fused; a phase offset, another constellation or an even
+    decision delay do not, and give the same answers through the two-kernel path."""
+    kw = path_kwargs("qpsk", sps=8)
+    hz = [700 + 411 * c for c in range(5)]
+    mb = pkg.Modem(**kw)
+    mb.set_channels([pkg.sample_freq(h, 10000) for h in hz], 4)
+    bits = rand_bits(78, 20, 2 * 700)
+    tx, sym, out, cnt, _ = _device_loopback(pkg, mb, bits)
+    for c in range(5):
+        oc = orc.OraclePath(**dict(kw, carrier_hz=hz[c]))
+        rows = slice(4 * c, 4 * c + 4)
+        assert_buffers(tx[rows], oc.modulate(bits[rows]), f"bank tx, channel {c}")
+        s_ref, b_ref, _ = oc.loopback(bits[rows])
+        assert np.array_equal(sym[rows], s_ref) and np.array_equal(out[rows], b_ref)
+    assert cnt[0] == 0 and cnt[1] == out.size
+    for over in (dict(phase_offset=0.3), dict(decision_delay=34), dict(scheme="bpsk")):
+        kw2 = dict(path_kwargs(over.get("scheme", "qpsk"), sps=8), **{k: v for k, v in over.items() if k != "scheme"})
+        m, o = make(pkg, orc, **kw2)
+        b = rand_bits(79, 6, o.bps * 900)
+        tx, sym, out, cnt, launches = _device_loopback(pkg, m, b) if o.bps == 2 else (None,) * 5
+        if tx is None:
+            got = m.loopback(b, want_tx=True)
+            tx, sym, out = got["tx"], got["sym"], got["bits"]
+        assert_buffers(tx, o.modulate(b), f"fallback tx {over}")
+        s_ref, b_ref, _ = o.loopback(b)
+        assert np.array_equal(sym, s_ref) and np.array_equal(out, b_ref), over
