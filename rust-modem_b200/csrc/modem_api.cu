@@ -534,6 +534,12 @@ bool loop_fused_eligible(modem_ctx* ctx, const uint8_t* d_bits, u64 F, u64 nbits
     a.F = F;
     a.K = modem_gpu_decided_symbols(ctx, a.L);
     if (F == 0 || a.L == 0 || a.K == 0 || a.L >= (1ull << 32)) return false;
+    { /* the kernel's symbol lookup: entry 3 = -entry 0 and entry 2 = -entry 1, bit for bit (true of qpsk.rs:23-35 at any phase) */
+        uint32_t u[8];
+        memcpy(u, ctx->h_const.data(), sizeof u);
+        if ((u[6] ^ u[0]) != 0x80000000u || (u[7] ^ u[1]) != 0x80000000u || (u[4] ^ u[2]) != 0x80000000u || (u[5] ^ u[3]) != 0x80000000u)
+            return false;
+    }
     a.delay = c.decision_delay;
     return mg::loop_fused_supported_64(a);
 }

@@ -268,6 +268,7 @@ __global__ void __launch_bounds__(THREADS, MINB)
      * (no phase offset: the launcher checks), so every buffer is bit-identical to the two-kernel path. */
     uint32_t sw[TXF ? C::ITER : 1]; /* the symbol's two bit bytes, per staged chunk */
     const bool first_tile = k0 == 0;
+    const float2 t1 = TXF ? a.tx_iq[1] : make_float2(0.0f, 0.0f);
     static_assert(!TXF || THREADS == 64, "symbol stride per step = 2*THREADS/8");
     /* -> the two bit bytes of this thread's first chunk: symbol (nbase + 2*tid) >> 3; chunk it*THREADS + tid: 16 symbols on per
      * step.  (Staging the tile's ~0.5 KB of bits through shared memory by cp.async, one frame ahead, measured 6 % slower
@@ -319,24 +320,31 @@ __global__ void __launch_bounds__(THREADS, MINB)
         }
         float parked[TMC > 0 ? TMC : 4];
         if (TMC > 0) tmem_ld32(twarp, parked);
-        if (TMC > 32) tmem_ld32(twarp + 32, parked + 32);
+        /* the fused form is short of registers in phase A (the symbol words are live too): it fetches the second half
+         * of the parked values only when the first has been used */
+        if (TMC > 32 && !TXF) tmem_ld32(twarp + 32, parked + 32);
 #pragma unroll
         for (int it = 0; it < C::ITER; ++it) {
+            if (TMC > 32 && TXF && it == 8) tmem_ld32(twarp + 32, parked + 32);
             if (it * THREADS + tid < C::NCHUNK) {
                 const float4 cs = (TMC > 0 && it < TCH) ? make_float4(parked[(4 * it) % (TMC > 0 ? TMC : 4)], parked[(4 * it + 1) % (TMC > 0 ? TMC : 4)], parked[(4 * it + 2) % (TMC > 0 ? TMC : 4)], parked[(4 * it + 3) % (TMC > 0 ? TMC : 4)])
                                                         : LDC(cs4 + it * THREADS);
                 if (TXF) {
+                    /* symbol index 2*b0 + b1 (first byte = MSB, digital/util.rs:5-11).  qpsk.rs:23-35 is odd in the pair of
+                     * signs, so entry 3 = -entry 0 and entry 2 = -entry 1 bit for bit (the launcher checks the table):
+                     * one select between entries 0 and 1, then the sign from b0 */
                     const uint32_t w = sw[TXF ? it : 0];
-                    const bool b0 = (w & 1u) != 0, b1 = (w & 0x100u) != 0; /* first byte = MSB (digital/util.rs:5-11) */
-                    const float si = b0 ? (b1 ? a.tx_iq[3].x : a.tx_iq[2].x) : (b1 ? a.tx_iq[1].x : a.tx_iq[0].x);
-                    const float sq = b0 ? (b1 ? a.tx_iq[3].y : a.tx_iq[2].y) : (b1 ? a.tx_iq[1].y : a.tx_iq[0].y);
+                    const bool mid = ((w ^ (w >> 8)) & 1u) != 0;
+                    const uint32_t sg = w << 31;
+                    const float si = __uint_as_float(__float_as_uint(mid ? t1.x : a.tx_iq[0].x) ^ sg);
+                    const float sq = __uint_as_float(__float_as_uint(mid ? t1.y : a.tx_iq[0].y) ^ sg);
                     const float2 x0 = mix_iq(si, sq, cs.x, cs.y), x1 = mix_iq(si, sq, cs.z, cs.w);
-                    const bool live = ((vmask >> it) & 1ull) != 0;
                     /* this tile owns local samples >= 8*(NB-1) (what the previous tile did not reach) */
                     const bool own = first_tile || it > 0 || tid >= 4 * (C::NB - 1);
-                    if (live && own && a.tx_out) __stcs(txrow + it * THREADS, make_float4(x0.x, x0.y, x1.x, x1.y));
-                    xr[it][0] = live ? x0.x : 0.0f;
-                    xr[it][1] = live ? x1.x : 0.0f;
+                    if (((vmask >> it) & 1ull) && own && a.tx_out) __stcs(txrow + it * THREADS, make_float4(x0.x, x0.y, x1.x, x1.y));
+                    /* outside the frame the NCO table holds zeros: x is +-0 there, like the zero the unfused kernel stages */
+                    xr[it][0] = x0.x;
+                    xr[it][1] = x1.x;
                 }
                 /* demodulator.rs:53-54: x*cos, x*(-sin); chunk q = it*THREADS + tid sits at position
                  * q + q/PADW = wbase + it*(THREADS + THREADS/PADW) */
