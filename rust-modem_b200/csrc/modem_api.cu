@@ -529,7 +529,7 @@ bool loop_fused_eligible(modem_ctx* ctx, const uint8_t* d_bits, u64 F, u64 nbits
     if (c.n_tx_taps || c.bits_per_symbol != 2 || c.n_tables != 1 || c.q_offset || c.samples_per_symbol != 8 || c.n_rx_taps != 64 ||
         (c.flags & MODEM_FLAG_FUSED_MAC) || !ctx->cs_rx_shared)
         return false;
-    if (!d_bits || (nbits & 1u) || (reinterpret_cast<uintptr_t>(d_bits) & 1u) || (d_tx && !aligned16(d_tx))) return false;
+    if (!d_bits || (nbits & 7u) || (reinterpret_cast<uintptr_t>(d_bits) & 7u) || (d_tx && !aligned16(d_tx))) return false; /* 8-byte rows of bits */
     a.L = (nbits / 2) * 8;
     a.F = F;
     a.K = modem_gpu_decided_symbols(ctx, a.L);

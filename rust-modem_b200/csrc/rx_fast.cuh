@@ -270,19 +270,44 @@ __global__ void __launch_bounds__(THREADS, MINB)
     const bool first_tile = k0 == 0;
     const float2 t1 = TXF ? a.tx_iq[1] : make_float2(0.0f, 0.0f);
     static_assert(!TXF || THREADS == 64, "symbol stride per step = 2*THREADS/8");
-    /* -> the two bit bytes of this thread's first chunk: symbol (nbase + 2*tid) >> 3; chunk it*THREADS + tid: 16 symbols on per
-     * step.  (Staging the tile's ~0.5 KB of bits through shared memory by cp.async, one frame ahead, measured 6 % slower
-     * than these direct loads: 0.692 against 0.654 ms at C2.) */
-    const uint8_t* brow = TXF ? a.ref_bits + f0 * a.ref_stride + 2 * ((nbase + 2 * (long long)tid) >> 3) : nullptr;
+    /* The tile's bit bytes (2 per symbol, NBLK symbols: ~0.5 KB) reach the threads through a small shared row: every
+     * thread fetches one 8-byte word of the NEXT frame's row when the FIR starts (two registers ride through the FIR),
+     * parks it in shared memory when the FIR is done, and phase A of the next frame picks its 2-byte symbols from
+     * there.  Direct 2-byte global loads at the top of the frame left 15 % of all stall samples on their latency
+     * (profiles/r01_fused_ncu.txt).  Rows start on 8-byte boundaries (the launcher checks). */
+    constexpr int BWORDS = (2 * C::NBLK + 7 + 7) / 8;
+    static_assert(!TXF || BWORDS <= 2 * THREADS, "two words per thread at most");
+    __shared__ __align__(8) unsigned long long s_bits[TXF ? BWORDS : 1];
+    const long long brow0 = (2 * (nbase >> 3)) & ~7ll; /* row offset of s_bits[0]; negative in the first tile */
+    /* this thread's first chunk: symbol (nbase + 2*tid) >> 3; chunk it*THREADS + tid: 16 symbols on per step */
+    const int boff = TXF ? (int)(2 * ((nbase + 2 * (long long)tid) >> 3) - brow0) : 0;
+    const uint8_t* brow = TXF ? a.ref_bits + f0 * a.ref_stride : nullptr;
     float4* txrow = TXF ? reinterpret_cast<float4*>(a.tx_out + f0 * a.L + nbase) + tid : nullptr;
+    unsigned long long nb0 = 0, nb1 = 0;
+    const long long bo0 = brow0 + 8 * tid, bo1 = bo0 + 8 * THREADS;
+    const bool bv0 = TXF && tid < BWORDS && bo0 >= 0 && bo0 + 8 <= (long long)a.ref_stride;
+    const bool bv1 = TXF && tid + THREADS < BWORDS && bo1 >= 0 && bo1 + 8 <= (long long)a.ref_stride;
+    auto fetch_bits = [&](const uint8_t* row) {
+        if (bv0) nb0 = __ldg(reinterpret_cast<const unsigned long long*>(row + bo0));
+        if (bv1) nb1 = __ldg(reinterpret_cast<const unsigned long long*>(row + bo1));
+    };
+    auto park_bits = [&]() {
+        if (bv0) s_bits[TXF ? tid : 0] = nb0;
+        if (bv1) s_bits[TXF ? tid + THREADS : 0] = nb1;
+    };
     auto load_syms = [&]() {
+        const unsigned char* sb = reinterpret_cast<const unsigned char*>(s_bits) + boff;
 #pragma unroll
         for (int it = 0; it < C::ITER; ++it) {
             uint32_t w = 0;
-            if ((vmask >> it) & 1ull) w = __ldg(reinterpret_cast<const uint16_t*>(brow + 32 * it));
+            if ((vmask >> it) & 1ull) w = *reinterpret_cast<const uint16_t*>(sb + 32 * it);
             sw[TXF ? it : 0] = w;
         }
     };
+    if (TXF && f0 < f1) {
+        fetch_bits(brow);
+        park_bits();
+    }
     if (PF == 2 && f0 < f1 && !TXF) load_tile(frame);
     for (u64 f = f0; f < f1; ++f, orow += a.K, frame += a.L) {
         __syncthreads(); /* previous frame's phase B finished; s_slut visible */
@@ -357,13 +382,7 @@ __global__ void __launch_bounds__(THREADS, MINB)
         if (TXF) {
             brow += a.ref_stride;
             txrow += a.L / 2;
-            /* the next frame's bits of this tile (2 B per symbol, ~0.5 KB) towards L2 while the FIR runs */
-            if (f + 1 < f1 && tid < (2 * C::NBLK + 127) / 128 + 1) {
-                const uint8_t* row = a.ref_bits + (f + 1) * a.ref_stride;
-                long long o = 2 * (nbase >> 3) + 128 * (long long)tid;
-                o = o < 0 ? 0 : (o >= (long long)a.ref_stride ? (long long)a.ref_stride - 1 : o);
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(row + o));
-            }
+            if (f + 1 < f1) fetch_bits(brow); /* the next frame's words fly during the FIR */
         }
         if (PF == 2 && f + 1 < f1 && !TXF) load_tile(frame + a.L); /* next frame's loads fly during the FIR */
         /* pull the next frame's tile towards L2 while the FIR runs: PF 1 = one prefetch per 128-byte
@@ -506,6 +525,7 @@ __global__ void __launch_bounds__(THREADS, MINB)
             }
         }
         if (refp) refp += a.ref_stride;
+        if (TXF && f + 1 < f1) park_bits(); /* read again only behind the barrier at the top of the next frame */
     }
     block_count(a, err, cmp);
     if (TMC > 0) tmem_free<(TMC > 0 ? TMC : 32)>(taddr);
