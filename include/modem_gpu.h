@@ -250,10 +250,13 @@ int modem_gpu_ber_sweep(modem_ctx_t* ctx, const uint8_t* bits, size_t F, size_t 
                         uint64_t* counters);
 
 /* loopback_device: the whole loopback, stream-ordered and device-resident (nothing is synchronised):
- * bits / tx (nullable => context scratch) / sym / bits_out (nullable) are device pointers, counters is
- * a DEVICE u64[2] that is accumulated into.  Internally the frames are cut into chunks of ~48 MB of
- * TX samples and the TX kernel of chunk c+1 runs on the context's stream while the RX kernel of chunk
- * c runs on a helper stream: the RX reads its chunk out of the 126 MB L2 instead of HBM. */
+ * bits / tx (nullable) / sym / bits_out (nullable) are device pointers, counters is a DEVICE u64[2] that is
+ * accumulated into.  The headline shape (QPSK table, rectangular hold, 8 samples per symbol, the 64-tap low-pass
+ * of src/bin/demodulate.rs:82-147, odd decision delay, exact MACs, sigma == 0, no phase offset, rows of bits on
+ * 8-byte boundaries) runs as ONE fused kernel that makes the TX samples, stores them to tx (not at all when tx is
+ * null) and demodulates them from registers; every buffer is bit-identical to the two-kernel path, which all other
+ * shapes take (tx null => context scratch).  MODEM_GPU_NO_FUSED_LOOP=1 forces two kernels; MODEM_GPU_LOOP_CHUNK=n
+ * cuts the two-kernel path into chunks of n frames with TX(c+1) || RX(c) on two streams (measured slower). */
 int modem_gpu_loopback_device(modem_ctx_t* ctx, const uint8_t* bits, size_t F, size_t nbits,
                               float sigma, uint64_t seed, uint64_t frame0, modem_c32_t* tx,
                               uint8_t* sym, uint8_t* bits_out, uint64_t* counters);
