@@ -104,6 +104,7 @@ struct modem_ctx {
     bool use_graph = true; /* MODEM_GPU_NO_GRAPH=1 disables */
     uint64_t launches = 0;
     bool force_generic = false;
+    bool pipe_fused = false; /* MODEM_GPU_PIPE_FUSED=1: the host-buffer pipeline uses the fused loopback kernel too */
     bool no_fused_loop = false; /* MODEM_GPU_NO_FUSED_LOOP=1: the loopback entries run the TX and the RX kernel separately */
     int rx_variant = 0; /* MODEM_GPU_RX_VARIANT: tuning knob, 0 = default */
     int rx_fpb = 0, rx_tile_major = -1; /* MODEM_GPU_RX_FPB / MODEM_GPU_RX_TILEMAJOR: tuning knobs */
@@ -822,6 +823,8 @@ int modem_gpu_create(modem_ctx_t** out, int device, const modem_cfg_t* cfg)
     ctx->cfg.tx_taps = cfg->n_tx_taps ? ctx->h_tx_taps.data() : nullptr;
     const char* fg = getenv("MODEM_GPU_FORCE_GENERIC");
     ctx->force_generic = fg && fg[0] == '1';
+    const char* pf = getenv("MODEM_GPU_PIPE_FUSED");
+    ctx->pipe_fused = pf && pf[0] == '1';
     const char* nf = getenv("MODEM_GPU_NO_FUSED_LOOP");
     ctx->no_fused_loop = nf && nf[0] == '1';
     const char* rv = getenv("MODEM_GPU_RX_VARIANT");
@@ -1255,8 +1258,15 @@ int loopback_pipelined(modem_ctx* ctx, const uint8_t* bits, size_t F, size_t nbi
         /* two kernels per chunk here: the fused loopback kernel (launch_loop_fused) measured SLOWER in this pipeline
          * (2.1 ms against 1.65 ms per step, with or without storing the samples) whenever the copy-out of the previous
          * chunk runs beside it; with the copy-out off both forms take 1.37 ms (tools/gpu_e2e_probe2.py) */
-        rc = launch_tx(ctx, (const uint8_t*)sl.bits.p, n, nbits, (float2*)ctx->pipe_tx.p, nullptr);
-        if (!rc)
+        bool fused = false;
+        if (ctx->pipe_fused) { /* MODEM_GPU_PIPE_FUSED=1: tuning knob, see above */
+            rc = launch_loop_fused(ctx, (const uint8_t*)sl.bits.p, n, nbits, nullptr, sym ? (uint8_t*)sl.sym.p : nullptr,
+                                   bits_out ? (uint8_t*)sl.out.p : nullptr, ctx->d_counters, sigma);
+            fused = rc == 1;
+            if (fused) rc = MODEM_OK;
+        }
+        if (!rc && !fused) rc = launch_tx(ctx, (const uint8_t*)sl.bits.p, n, nbits, (float2*)ctx->pipe_tx.p, nullptr);
+        if (!rc && !fused)
             rc = launch_rx(ctx, (const float2*)ctx->pipe_tx.p, n, L, sym ? (uint8_t*)sl.sym.p : nullptr,
                            bits_out ? (uint8_t*)sl.out.p : nullptr, nullptr, nullptr, (const uint8_t*)sl.bits.p, nbits,
                            ctx->d_counters, sigma, seed, frame0 + fs);

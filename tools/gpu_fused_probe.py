@@ -6,7 +6,7 @@ pkg = g.load_package()
 lp = pkg.lowpass_taps()
 kw = dict(scheme="qpsk", baud_rate=1250, sample_rate=10000, carrier_hz=2500, decision_delay=35, slicer_gain=float(lp.sum()), rx_taps=lp)
 NB = 16384
-for F in (64, 128, 256, 512, 1024, 4096):
+for F in ((4096,) if os.environ.get("MODEM_GPU_RX_FPB") else (64, 128, 256, 512, 1024, 4096)):
     m = pkg.Modem(**kw)
     st = torch.cuda.current_stream(); m.set_stream(st.cuda_stream)
     L = m.frame_samples(NB); K = m.decided_symbols(L)
