@@ -1483,7 +1483,7 @@ int modem_gpu_loopback(modem_ctx_t* ctx, const uint8_t* bits, size_t F, size_t n
     const size_t K = modem_gpu_decided_symbols(ctx, L);
     const size_t bps = ctx->cfg.bits_per_symbol;
     if (!tx && L && !is_device_ptr(bits) && !is_device_ptr(sym) && !is_device_ptr(bits_out)) {
-        /* host buffers and no TX dump requested: chunked three-lane pipeline */
+        /* host buffers and no TX dump requested: chunked pipeline (copy-in, kernels, copy-out streams) */
         size_t Fc = ctx->pipe_chunk ? ctx->pipe_chunk : std::max<size_t>(1, ((size_t)128 << 20) / (L * sizeof(float2)));
         if (ctx->n_channels) { /* chunk boundaries on channel boundaries (or whole divisors of them) */
             const size_t fc = ctx->frames_per_channel;
