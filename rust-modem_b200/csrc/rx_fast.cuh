@@ -21,6 +21,9 @@
  *           (NB+R-1)*64 B per R symbols: 22 B/sample at R = 4, NT = 64;
  *  phase C  slice, pack, count errors; one R-byte symbol store and one 2R-byte bit store per thread.
  *
+ *  TXF      (template flag) the fused loopback: phase A makes the tile's TX samples from the frame's bits instead of
+ *           loading them, stores them once, and mixes them from registers -- see the block comment in the kernel.
+ *
  * Shared layout: 16-byte chunk c (samples 2c, 2c+1) lives at chunk position c + c/(4R): one
  * chunk of padding per thread stride, so the 8 lanes of a quarter warp (stride 4R chunks in
  * phase B, stride 1 in phase A) always hit 8 distinct bank groups.
