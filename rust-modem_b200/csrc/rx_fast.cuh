@@ -34,6 +34,9 @@
 
 namespace mg {
 
+#ifndef MG_TXF_PACKED_MIX
+#define MG_TXF_PACKED_MIX 1
+#endif
 #ifndef MG_RX_LDMODE
 #define MG_RX_LDMODE 3
 #endif
@@ -366,7 +369,16 @@ __global__ void __launch_bounds__(THREADS, MINB)
                     const uint32_t sg = w << 31;
                     const float si = __uint_as_float(__float_as_uint(mid ? t1.x : a.tx_iq[0].x) ^ sg);
                     const float sq = __uint_as_float(__float_as_uint(mid ? t1.y : a.tx_iq[0].y) ^ sg);
+#if MG_TXF_PACKED_MIX
+                    /* modulator.rs:37-43 on packed pairs: (i*c, i*s) and (q*s, q*c) by two FMUL2, then
+                     * (i*c - q*s, i*s + q*c) by one FFMA2 with (-1, +1): a product by +-1 is exact, so the fma's one
+                     * rounding is the rounding of the reference's subtraction / addition */
+                    const f32x2 ii = pk2(si, si), qq = pk2(sq, sq), pm = pk2(-1.0f, 1.0f);
+                    const float2 x0 = unpk2(fma2(mul2(qq, pk2(cs.y, cs.x)), pm, mul2(ii, pk2(cs.x, cs.y))));
+                    const float2 x1 = unpk2(fma2(mul2(qq, pk2(cs.w, cs.z)), pm, mul2(ii, pk2(cs.z, cs.w))));
+#else
                     const float2 x0 = mix_iq(si, sq, cs.x, cs.y), x1 = mix_iq(si, sq, cs.z, cs.w);
+#endif
                     /* this tile owns local samples >= 8*(NB-1) (what the previous tile did not reach) */
                     const bool own = first_tile || it > 0 || tid >= 4 * (C::NB - 1);
                     if (((vmask >> it) & 1ull) && own && a.tx_out) __stcs(txrow + it * THREADS, make_float4(x0.x, x0.y, x1.x, x1.y));
