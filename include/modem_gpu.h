@@ -58,6 +58,14 @@ typedef struct modem_comm modem_comm_t;
                                      separate mul+add (fir.rs:23).  Faster on long taps, no
                                      longer bit-identical to the CPU path (still << 1e-5). */
 
+#define MODEM_FLAG_NO_TMEM 0x2u   /* The tuned sps-8 RX / fused loopback kernels park frame-invariant NCO values in
+                                     TENSOR MEMORY (tcgen05.alloc: 64 columns per CTA, 256 of an SM's 512 columns for the
+                                     fused kernel, all 512 for the plain 64-tap RX kernel at 8 CTAs per SM).
+                                     tcgen05.alloc blocks until columns are free, so next to another tensor-memory user
+                                     on the same device (a tcgen05 GEMM on another stream) these kernels can serialise
+                                     with it.  This flag selects instantiations that allocate no tensor memory (the
+                                     values are read through L1 instead: ~10 % slower, bit-identical results). */
+
 /*
  * Path configuration.  Field names follow the reference's parameter vocabulary.
  */

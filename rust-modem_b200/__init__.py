@@ -9,10 +9,10 @@ sm_100 GPU every compute call raises.
 """
 from . import capi
 from .capi import (ModemError, Modem, ModemCfg, lib, build_library, library_path, host_constellation,
-                   lowpass_taps, rrc_taps, hilbert_taps, host_phasor, Phasor, sample_freq, samples_per_symbol, FLAG_FUSED_MAC,
+                   lowpass_taps, rrc_taps, hilbert_taps, host_phasor, Phasor, sample_freq, samples_per_symbol, FLAG_FUSED_MAC, FLAG_NO_TMEM,
                    STATEFUL_NAMES)
 
 from .sharding import shard_range, shard_channels
 
 __all__ = ["shard_range", "shard_channels", "ModemError", "Modem", "ModemCfg", "lib", "build_library", "library_path", "host_constellation",
-           "lowpass_taps", "rrc_taps", "hilbert_taps", "host_phasor", "Phasor", "STATEFUL_NAMES", "sample_freq", "samples_per_symbol", "FLAG_FUSED_MAC"]
+           "lowpass_taps", "rrc_taps", "hilbert_taps", "host_phasor", "Phasor", "STATEFUL_NAMES", "sample_freq", "samples_per_symbol", "FLAG_FUSED_MAC", "FLAG_NO_TMEM"]

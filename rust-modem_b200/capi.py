@@ -9,6 +9,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _SO = os.path.join(_HERE, "lib", "libmodem_gpu.so")
 
 FLAG_FUSED_MAC = 0x1
+FLAG_NO_TMEM = 0x2
 COMM_ID_BYTES = 128
 
 

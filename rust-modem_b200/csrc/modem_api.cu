@@ -105,8 +105,8 @@ struct modem_ctx {
     uint64_t launches = 0;
     bool force_generic = false;
     bool pipe_fused = false; /* MODEM_GPU_PIPE_FUSED=1: the host-buffer pipeline uses the fused loopback kernel too */
+    bool no_sign_slice = false; /* MODEM_GPU_NO_SIGN_SLICE=1: the fast RX kernel always runs the nearest-point search */
     bool no_fused_loop = false; /* MODEM_GPU_NO_FUSED_LOOP=1: the loopback entries run the TX and the RX kernel separately */
-    int rx_variant = 0; /* MODEM_GPU_RX_VARIANT: tuning knob, 0 = default */
     int rx_fpb = 0, rx_tile_major = -1; /* MODEM_GPU_RX_FPB / MODEM_GPU_RX_TILEMAJOR: tuning knobs */
     size_t pipe_chunk = 0; /* MODEM_GPU_PIPE_CHUNK: frames per pipeline chunk (0 = ~64 MB of TX samples) */
     std::string last_error;
@@ -241,6 +241,13 @@ uint32_t frames_per_block(const modem_ctx* ctx, u64 F, u64 tiles_x)
 
 bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
+/* Sign slicer of the fast RX kernel (rx_fast.cuh phase C).  Eligible when the gain-scaled slicer table is the four points
+ * (-+A, -+B) in index order (bit 1 of the index = sign of i, bit 0 = sign of q: qpsk.rs:23-35 at phase 0), A and B
+ * positive, finite and within a factor 2 of each other.  For soft values with |I|, |Q| in [min/1024, 4 min] the sign
+ * test then returns exactly what the nearest-point search returns, roundings and tie rule included (the proof is in
+ * DESIGN.md section 4); outside that window the kernel runs the search. */
+void set_sign_slicer(const modem_ctx* ctx, mg::RxArgs& a);
+
 /*
  * Make sure the NCO tables cover the channels of frames [frame_base, frame_base + F) at `len` samples
  * per frame, then point the view at the TX (rx == false) or RX table.  One tiny kernel per new key.
@@ -286,6 +293,24 @@ int attach_carrier_table(modem_ctx* ctx, mg::ChannelView& view, u64 F, u64 len, 
     view.cs_len = kCsPadLo + len + kCsPadHi;
     view.cs_ch0 = key.ch0;
     return MODEM_OK;
+}
+
+void set_sign_slicer(const modem_ctx* ctx, mg::RxArgs& a)
+{
+    a.sign_slice = 0;
+    a.ss_lo = a.ss_hi = 0.0f;
+    if (ctx->no_sign_slice || ctx->cfg.bits_per_symbol != 2 || ctx->cfg.n_tables != 1 || ctx->h_slut.size() != 8) return;
+    const float A = ctx->h_slut[6], B = ctx->h_slut[7]; /* entry 3 = (+A, +B) */
+    if (!(A > 0.0f) || !(B > 0.0f) || !std::isfinite(A) || !std::isfinite(B)) return;
+    const float mn = std::min(A, B), mx = std::max(A, B);
+    if (mx > 2.0f * mn || mn < 1e-30f || mx > 1e30f) return;
+    for (int j = 0; j < 4; ++j) {
+        const float wi = (j & 2) ? A : -A, wq = (j & 1) ? B : -B;
+        if (memcmp(&wi, &ctx->h_slut[2 * j], 4) || memcmp(&wq, &ctx->h_slut[2 * j + 1], 4)) return;
+    }
+    a.sign_slice = 1;
+    a.ss_lo = mn * (1.0f / 1024.0f);
+    a.ss_hi = 4.0f * mn;
 }
 
 /* ------------------------------------------------------------------ TX launch */
@@ -471,7 +496,7 @@ int launch_rx(modem_ctx* ctx, const float2* d_rx, u64 F, u64 L, uint8_t* d_sym, 
     const bool fast_ok = !src && !ctx->force_generic && sps == 8 && c.q_offset == 0 && (L % 2 == 0) && aligned16(d_rx) &&
                          mg::rx_fast_supported(N);
     if (fast_ok) {
-        a.frames_per_block = frames_per_block(ctx, F, mg::rx_fast_tiles(N, a.K, ctx->rx_variant));
+        a.frames_per_block = frames_per_block(ctx, F, mg::rx_fast_tiles(N, a.K));
         if (ctx->rx_fpb > 0 && !ctx->n_channels) a.frames_per_block = (uint32_t)std::max<u64>(ctx->rx_fpb, (F + 65534) / 65535);
         else a.frames_per_block = std::min<uint32_t>(a.frames_per_block, 16); /* measured: 8..16 is the sweet spot once the NCO table removed the per-CTA setup */
         if (ctx->n_channels) while (ctx->frames_per_channel % a.frames_per_block || ctx->frame_base % a.frames_per_block) --a.frames_per_block;
@@ -479,7 +504,8 @@ int launch_rx(modem_ctx* ctx, const float2* d_rx, u64 F, u64 L, uint8_t* d_sym, 
         int rc = attach_carrier_table(ctx, a.ch, F, L, true);
         if (rc) return rc;
         if (!a.ch.cs_tab) return fail(ctx, MODEM_ERR_UNSUPPORTED, "carrier bank too large for the NCO table (> 1 GiB)");
-        CK(ctx, mg::rx_fast_launch(a, ctx->h_rx_taps.data(), fma, ctx->rx_variant, ctx->stream));
+        set_sign_slicer(ctx, a);
+        CK(ctx, mg::rx_fast_launch(a, ctx->h_rx_taps.data(), fma, !(c.flags & MODEM_FLAG_NO_TMEM), ctx->stream));
     } else {
         size_t budget = 96 * 1024;
         if ((size_t)N * 4 + (size_t)(N + c.q_offset) * 17 + 64 > budget)
@@ -517,8 +543,8 @@ int launch_rx(modem_ctx* ctx, const float2* d_rx, u64 F, u64 L, uint8_t* d_sym, 
 /*
  * Fused loopback: one kernel makes the TX samples of a tile from the bits, stores them (the TX buffer the caller
  * gets is the same, bit for bit) and demodulates them from registers -- the RX side's 8 B/sample read is gone.
- * Eligible: the headline shape (QPSK table, rectangular hold, sps 8, the 64-tap low-pass, odd decision delay, exact
- * MACs, no noise, no phase offset anywhere so that both sides share one NCO table).  Returns 1 = launched,
+ * Eligible: the headline shape (any one 4-point table -- QPSK at any phase --, rectangular hold, sps 8, the 64-tap low-pass,
+ * odd decision delay, exact MACs, no noise, no phase offset anywhere so that both sides share one NCO table).  Returns 1 = launched,
  * 0 = not eligible (the caller runs the two kernels), < 0 = error.
  */
 /* the shape test of the fused loopback; fills the geometry of `a`.  d_tx may be null: the samples are then not stored
@@ -526,7 +552,7 @@ int launch_rx(modem_ctx* ctx, const float2* d_rx, u64 F, u64 L, uint8_t* d_sym, 
 bool loop_fused_eligible(modem_ctx* ctx, const uint8_t* d_bits, u64 F, u64 nbits, const float2* d_tx, float sigma, mg::RxArgs& a)
 {
     const modem_cfg_t& c = ctx->cfg;
-    if (ctx->no_fused_loop || ctx->force_generic || ctx->phasor_on || ctx->rx_variant || sigma != 0.0f) return false;
+    if (ctx->no_fused_loop || ctx->force_generic || ctx->phasor_on || sigma != 0.0f) return false;
     if (c.n_tx_taps || c.bits_per_symbol != 2 || c.n_tables != 1 || c.q_offset || c.samples_per_symbol != 8 || c.n_rx_taps != 64 ||
         (c.flags & MODEM_FLAG_FUSED_MAC) || !ctx->cs_rx_shared)
         return false;
@@ -535,12 +561,6 @@ bool loop_fused_eligible(modem_ctx* ctx, const uint8_t* d_bits, u64 F, u64 nbits
     a.F = F;
     a.K = modem_gpu_decided_symbols(ctx, a.L);
     if (F == 0 || a.L == 0 || a.K == 0 || a.L >= (1ull << 32)) return false;
-    { /* the kernel's symbol lookup: entry 3 = -entry 0 and entry 2 = -entry 1, bit for bit (true of qpsk.rs:23-35 at any phase) */
-        uint32_t u[8];
-        memcpy(u, ctx->h_const.data(), sizeof u);
-        if ((u[6] ^ u[0]) != 0x80000000u || (u[7] ^ u[1]) != 0x80000000u || (u[4] ^ u[2]) != 0x80000000u || (u[5] ^ u[3]) != 0x80000000u)
-            return false;
-    }
     a.delay = c.decision_delay;
     return mg::loop_fused_supported_64(a);
 }
@@ -577,7 +597,8 @@ int launch_loop_fused(modem_ctx* ctx, const uint8_t* d_bits, u64 F, u64 nbits, f
     int rc = attach_carrier_table(ctx, a.ch, F, a.L, true);
     if (rc) return rc;
     if (!a.ch.cs_tab) return 0;
-    cudaError_t e = mg::loop_fused_launch_64(a, ctx->h_rx_taps.data(), ctx->stream);
+    set_sign_slicer(ctx, a);
+    cudaError_t e = mg::loop_fused_launch_64(a, ctx->h_rx_taps.data(), !(c.flags & MODEM_FLAG_NO_TMEM), ctx->stream);
     if (e != cudaSuccess) return fail(ctx, MODEM_ERR_CUDA, std::string("fused loopback: ") + cudaGetErrorString(e));
     ctx->launches++;
     return 1;
@@ -827,8 +848,8 @@ int modem_gpu_create(modem_ctx_t** out, int device, const modem_cfg_t* cfg)
     ctx->pipe_fused = pf && pf[0] == '1';
     const char* nf = getenv("MODEM_GPU_NO_FUSED_LOOP");
     ctx->no_fused_loop = nf && nf[0] == '1';
-    const char* rv = getenv("MODEM_GPU_RX_VARIANT");
-    ctx->rx_variant = rv ? atoi(rv) : 0;
+    const char* nss = getenv("MODEM_GPU_NO_SIGN_SLICE");
+    ctx->no_sign_slice = nss && nss[0] == '1';
     const char* rf = getenv("MODEM_GPU_RX_FPB");
     ctx->rx_fpb = rf ? atoi(rf) : 0;
     const char* tm = getenv("MODEM_GPU_RX_TILEMAJOR");

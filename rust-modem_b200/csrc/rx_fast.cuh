@@ -30,6 +30,9 @@
  */
 #pragma once
 
+#include <atomic>
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace mg {
@@ -176,11 +179,14 @@ __global__ void __launch_bounds__(THREADS, MINB)
     rx_fast_kernel(const __grid_constant__ RxArgs a, const __grid_constant__ TapsParam<NT> taps)
 {
     using C = RxFastCfg<NT, OFF, THREADS, R>;
+    static_assert((THREADS & (THREADS - 1)) == 0, "tid is masked to THREADS - 1 so that ptxas can drop the per-chunk range checks");
+    static_assert(C::ITER <= 64, "one validity bit per staged chunk");
+    using vmask_t = typename std::conditional<(C::ITER > 32), unsigned long long, uint32_t>::type;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    float4* s_v = reinterpret_cast<float4*>(smem_raw); /* padded chunks of (vi0,vq0,vi1,vq1) */
+    ulonglong2* s_v = reinterpret_cast<ulonglong2*>(smem_raw); /* padded chunks of packed pairs (vi0,vq0), (vi1,vq1) */
     float2* s_slut = reinterpret_cast<float2*>(s_v + C::PCHUNK);
 
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x & (THREADS - 1);
     for (uint32_t i = tid; i < a.n_tables * a.n_const; i += THREADS) s_slut[i] = a.slut[i];
 
     /* tile-major launch order (blockIdx.x = frame group) makes the CTAs that are resident together work on
@@ -194,6 +200,9 @@ __global__ void __launch_bounds__(THREADS, MINB)
      * nbase are even, so a 16-byte pair is either entirely inside the frame or entirely outside */
     const long long vlo_n = nbase < 0 ? 0 : nbase;
     const long long vhi_n = (u64)(nbase + C::NSAMP) > a.L ? (long long)a.L : nbase + C::NSAMP;
+    /* INTERIOR tiles (every staged sample exists in the frame: all but the first and the last tile of a frame) run a
+     * phase A without any per-chunk validity test; the noisy and the register-prefetch forms always take the edge form */
+    const bool edge = NOISE || PF == 2 || nbase < 0 || (u64)(nbase + C::NSAMP) > a.L;
 
     /* NCO values of the tile: read every frame from the zero-padded global table (ChannelView::cs_tab).
      * The tile's 17 KB slice stays L1/L2-resident across the frame loop, costs no shared memory and no
@@ -204,7 +213,7 @@ __global__ void __launch_bounds__(THREADS, MINB)
     __shared__ uint32_t s_tmem;
     uint32_t taddr = 0, twarp = 0;
     if (TMC > 0) {
-        static_assert(TMC == 0 || TMC == 32 || TMC == 64, "one or two tcgen05 32x32b.x32 transfers per thread");
+        static_assert(TMC == 0 || TMC == 32 || TMC == 64 || TMC == 128, "one, two or four tcgen05 32x32b.x32 transfers per thread");
         static_assert(TMC == 0 || THREADS <= 128, "a CTA reaches TMEM lanes 32*(warp % 4)");
         taddr = tmem_alloc<(TMC > 0 ? TMC : 32)>(&s_tmem);
         twarp = tmem_warp_addr(taddr);
@@ -240,86 +249,104 @@ __global__ void __launch_bounds__(THREADS, MINB)
 
     uint32_t err = 0, cmp = 0;
     const int wbase = tid + tid / C::PADW;              /* phase A: chunk position of chunk `tid` */
-    const ulonglong2* rbase = reinterpret_cast<const ulonglong2*>(s_v) + (C::PADW + 1) * tid; /* phase B: chunk position of chunk 4R*tid */
+    const ulonglong2* rbase = s_v + (C::PADW + 1) * tid; /* phase B: chunk position of chunk 4R*tid */
     const f32x2 one = pk2(taps.one.x, taps.one.y);
     const float2* frame = a.rx + f0 * a.L;
     u64 orow = f0 * a.K + ka; /* output index of symbol ka in the current frame */
     const uint8_t* refp = a.ref_bits ? a.ref_bits + f0 * a.ref_stride + ka * 2 : nullptr;
     float xr[C::ITER][2]; /* real parts of the tile being staged (PF == 2: of the NEXT frame, in flight during the FIR) */
-    /* which of this thread's chunks exist in the frame: one bit per step, fixed for the whole frame loop, so
+    /* which of this thread's chunks exist in the frame (edge tiles): one bit per step, fixed for the whole frame loop, so
      * the loads below are predicated, never branched around (a branch would make ptxas drain outstanding
      * loads at the join and defeat any prefetch) */
-    unsigned long long vmask = 0;
+    vmask_t vmask = 0;
 #pragma unroll
     for (int it = 0; it < C::ITER; ++it) {
         const long long n = nbase + 2 * (it * THREADS + tid);
-        if (it * THREADS + tid < C::NCHUNK && n >= vlo_n && n < vhi_n) vmask |= 1ull << it;
+        if (it * THREADS + tid < C::NCHUNK && n >= vlo_n && n < vhi_n) vmask |= (vmask_t)1 << it;
     }
-    auto load_tile = [&](const float2* fr) {
+    /* does step `it` stage a chunk at all?  Only the last step is partial, and by a compile-time thread count */
+    auto staged = [&](int it) { return (it + 1) * THREADS <= C::NCHUNK || tid < C::NCHUNK - it * THREADS; };
+    auto load_tile = [&](const float2* fr, auto edge_c) {
+        constexpr bool EDGE = decltype(edge_c)::value;
         const float4* src = reinterpret_cast<const float4*>(fr + nbase) + tid;
 #pragma unroll
         for (int it = 0; it < C::ITER; ++it) {
             float4 t = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-            if ((vmask >> it) & 1ull) t = LDX(src + it * THREADS);
+            if (EDGE ? ((vmask >> it) & 1) != 0 : staged(it)) t = LDX(src + it * THREADS);
             xr[it][0] = t.x;
             xr[it][1] = t.z;
         }
     };
     /* ---- TXF: the fused loopback.  The tile's TX samples are not read from memory but MADE here, from the frame's
-     * bits (a.ref_bits, two bytes per QPSK symbol) with the arithmetic of the rectangular-hold TX kernel
-     * (data.rs:66-79 hold, qpsk.rs:23-35 table, modulator.rs:37-48 mix: re = i*cos - q*sin, im = i*sin + q*cos, each
-     * operation rounded on its own), stored to a.tx_out exactly once (a tile owns the samples behind its halo; the
-     * first tile also owns the frame's head) and fed to the demodulator from registers: the 8 B/sample read of the
-     * RX side disappears, the loopback is one pass of 8 B/sample written + bits.  Same NCO values on both sides
-     * (no phase offset: the launcher checks), so every buffer is bit-identical to the two-kernel path. */
-    uint32_t sw[TXF ? C::ITER : 1]; /* the symbol's two bit bytes, per staged chunk */
+     * bits (a.ref_bits, two bytes per symbol) with the arithmetic of the rectangular-hold TX kernel
+     * (data.rs:66-79 hold, digital/qpsk.rs:23-35 as a 4-entry table, modulator.rs:37-48 mix: re = i*cos - q*sin,
+     * im = i*sin + q*cos, each operation rounded on its own), stored to a.tx_out exactly once (a tile owns the samples
+     * behind its halo; the first tile also owns the frame's head) and fed to the demodulator from registers: the
+     * 8 B/sample read of the RX side disappears, the loopback is one pass of 8 B/sample written + bits.  Same NCO values
+     * on both sides (no phase offset: the launcher checks), so every buffer is bit-identical to the two-kernel path. */
     const bool first_tile = k0 == 0;
-    const float2 t1 = TXF ? a.tx_iq[1] : make_float2(0.0f, 0.0f);
-    static_assert(!TXF || THREADS == 64, "symbol stride per step = 2*THREADS/8");
-    /* The tile's bit bytes (2 per symbol, NBLK symbols: ~0.5 KB) reach the threads through a small shared row: every
-     * thread fetches one 8-byte word of the NEXT frame's row when the FIR starts (two registers ride through the FIR),
-     * parks it in shared memory when the FIR is done, and phase A of the next frame picks its 2-byte symbols from
-     * there.  Direct 2-byte global loads at the top of the frame left 15 % of all stall samples on their latency
-     * (profiles/r01_fused_ncu.txt).  Rows start on 8-byte boundaries (the launcher checks). */
+    const bool store_tx = TXF && a.tx_out != nullptr;
+    static_assert(!TXF || THREADS % 4 == 0, "symbol stride per step = 2*THREADS/8");
+    /* The tile's symbols reach the threads through a small shared table of (i, q) PAIRS, one per symbol the tile touches:
+     * every thread fetches one 8-byte word (4 symbols of 2 bit bytes) of the NEXT frame's row when the FIR starts (two
+     * registers ride through the FIR), maps its 4 symbols through the constellation table (a.tx_iq, a constant-bank
+     * lookup by the symbol index 2*b0 + b1: first byte = MSB, digital/util.rs:5-11) when the FIR is done and parks the
+     * pairs in shared memory; phase A of the next frame then needs ONE 8-byte shared load per staged chunk and no bit
+     * arithmetic.  (Round 1: 2-byte loads and select/sign logic per CHUNK, 8 instructions x 17 chunks per thread and
+     * frame.)  Rows start on 8-byte boundaries (the launcher checks). */
     constexpr int BWORDS = (2 * C::NBLK + 7 + 7) / 8;
-    static_assert(!TXF || BWORDS <= 2 * THREADS, "two words per thread at most");
-    __shared__ __align__(8) unsigned long long s_bits[TXF ? BWORDS : 1];
-    const long long brow0 = (2 * (nbase >> 3)) & ~7ll; /* row offset of s_bits[0]; negative in the first tile */
-    /* this thread's first chunk: symbol (nbase + 2*tid) >> 3; chunk it*THREADS + tid: 16 symbols on per step */
-    const int boff = TXF ? (int)(2 * ((nbase + 2 * (long long)tid) >> 3) - brow0) : 0;
+    constexpr int WPT = (BWORDS + THREADS - 1) / THREADS; /* words per thread: 2 (3 at R = 8) */
+    __shared__ __align__(16) f32x2 s_sq[TXF ? 4 * BWORDS : 2];
+    const long long brow0 = (2 * (nbase >> 3)) & ~7ll; /* row byte offset of table entry 0; negative in the first tile */
+    /* this thread's first chunk lies in symbol (nbase + 2*tid) >> 3; chunk it*THREADS + tid: THREADS/4 symbols on per step */
+    const int sqoff = TXF ? (int)(((nbase + 2 * (long long)tid) >> 3) - (brow0 >> 1)) : 0;
     const uint8_t* brow = TXF ? a.ref_bits + f0 * a.ref_stride : nullptr;
     float4* txrow = TXF ? reinterpret_cast<float4*>(a.tx_out + f0 * a.L + nbase) + tid : nullptr;
-    unsigned long long nb0 = 0, nb1 = 0;
-    const long long bo0 = brow0 + 8 * tid, bo1 = bo0 + 8 * THREADS;
-    const bool bv0 = TXF && tid < BWORDS && bo0 >= 0 && bo0 + 8 <= (long long)a.ref_stride;
-    const bool bv1 = TXF && tid + THREADS < BWORDS && bo1 >= 0 && bo1 + 8 <= (long long)a.ref_stride;
+    unsigned long long nb[WPT];
+    /* word w of this thread = table word tid + w*THREADS at row byte offset bo0 + 8*w*THREADS.  Which of them lie inside
+     * the row: flag bits kept in ONE register the compiler cannot see through (it otherwise re-derives the 64-bit
+     * comparisons every frame) */
+    const long long bo0 = brow0 + 8 * tid;
+    uint32_t bvf = 0;
+#pragma unroll
+    for (int w = 0; w < WPT; ++w) {
+        const long long bo = bo0 + 8ll * w * THREADS;
+        nb[w] = 0;
+        if (TXF && tid + w * THREADS < BWORDS && bo >= 0 && bo + 8 <= (long long)a.ref_stride) bvf |= 1u << w;
+    }
+    asm volatile("" : "+r"(bvf));
     auto fetch_bits = [&](const uint8_t* row) {
-        if (bv0) nb0 = __ldg(reinterpret_cast<const unsigned long long*>(row + bo0));
-        if (bv1) nb1 = __ldg(reinterpret_cast<const unsigned long long*>(row + bo1));
+#pragma unroll
+        for (int w = 0; w < WPT; ++w) {
+            nb[w] = 0; /* symbols outside the frame map to entry 0: finite, and multiplied by the NCO table's zeros */
+            if (bvf & (1u << w)) nb[w] = __ldg(reinterpret_cast<const unsigned long long*>(row + bo0 + 8ll * w * THREADS));
+        }
+    };
+    auto map_word = [&](unsigned long long w, f32x2* dst) {
+        f32x2 e[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const uint32_t h = (uint32_t)(w >> (16 * j));
+            const float2 p = a.tx_iq[((h & 1u) << 1) | ((h >> 8) & 1u)];
+            e[j] = pk2(p.x, p.y);
+        }
+        reinterpret_cast<ulonglong2*>(dst)[0] = make_ulonglong2(e[0], e[1]);
+        reinterpret_cast<ulonglong2*>(dst)[1] = make_ulonglong2(e[2], e[3]);
     };
     auto park_bits = [&]() {
-        if (bv0) s_bits[TXF ? tid : 0] = nb0;
-        if (bv1) s_bits[TXF ? tid + THREADS : 0] = nb1;
-    };
-    auto load_syms = [&]() {
-        const unsigned char* sb = reinterpret_cast<const unsigned char*>(s_bits) + boff;
 #pragma unroll
-        for (int it = 0; it < C::ITER; ++it) {
-            uint32_t w = 0;
-            if ((vmask >> it) & 1ull) w = *reinterpret_cast<const uint16_t*>(sb + 32 * it);
-            sw[TXF ? it : 0] = w;
-        }
+        for (int w = 0; w < WPT; ++w)
+            if (TXF && ((w + 1) * THREADS <= BWORDS || tid + w * THREADS < BWORDS)) map_word(nb[w], s_sq + (TXF ? 4 * (tid + w * THREADS) : 0));
     };
     if (TXF && f0 < f1) {
         fetch_bits(brow);
         park_bits();
     }
-    if (PF == 2 && f0 < f1 && !TXF) load_tile(frame);
-    for (u64 f = f0; f < f1; ++f, orow += a.K, frame += a.L) {
-        __syncthreads(); /* previous frame's phase B finished; s_slut visible */
-        /* ---- phase A: load the tile (all loads issued before the first use), mix, stage */
-        if (TXF) load_syms();
-        else if (PF != 2) load_tile(frame);
+    /* ---- phase A: load the tile (all loads issued before the first use), mix, stage.  EDGE = the tile reaches past a
+     * frame end (validity bits per chunk), else every chunk exists and only the last step is partial */
+    auto phase_a = [&](const float2* fr, u64 f, auto edge_c) {
+        constexpr bool EDGE = decltype(edge_c)::value;
+        if (!TXF && PF != 2) load_tile(fr, edge_c);
         if (NOISE) {
             /* G chunks per trip: their Philox / logf / sqrt / sincos chains are independent, so the scheduler can
              * interleave them (one chunk per trip left ~2 independent chains per warp at 4 warps per scheduler:
@@ -349,57 +376,69 @@ __global__ void __launch_bounds__(THREADS, MINB)
                         }
             }
         }
-        float parked[TMC > 0 ? TMC : 4];
-        if (TMC > 0) tmem_ld32(twarp, parked);
-        /* the fused form is short of registers in phase A (the symbol words are live too): it fetches the second half
-         * of the parked values only when the first has been used */
-        if (TMC > 32 && !TXF) tmem_ld32(twarp + 32, parked + 32);
+        /* the chunk's symbol pair (one 8-byte shared load per step) is fetched SQD steps ahead of its use: next to its use
+         * it cost a shared-memory round trip per chunk (19 % of all stall samples; the compiler does not hoist it above
+         * the previous step's shared store by itself), all 17 up front cost 34 registers */
+        constexpr int SQD = THREADS >= 128 ? 0 : 3; /* measured: the 4-warp CTA is 4 % faster without the look-ahead, the 2-warp CTA 4 % slower */
+        f32x2 sqv[TXF ? C::ITER : 1];
+        auto sq_fetch = [&](int it) {
+            if (TXF && it < C::ITER && staged(it)) sqv[TXF ? it : 0] = s_sq[TXF ? sqoff + (THREADS / 4) * it : 0];
+        };
+#pragma unroll
+        for (int it = 0; it < SQD; ++it) sq_fetch(it);
+        /* the parked NCO values come back 32 columns (8 steps) at a time, each batch when the previous one is used up */
+        float parked[TMC > 0 ? 32 : 4];
 #pragma unroll
         for (int it = 0; it < C::ITER; ++it) {
-            if (TMC > 32 && TXF && it == 8) tmem_ld32(twarp + 32, parked + 32);
-            if (it * THREADS + tid < C::NCHUNK) {
-                const float4 cs = (TMC > 0 && it < TCH) ? make_float4(parked[(4 * it) % (TMC > 0 ? TMC : 4)], parked[(4 * it + 1) % (TMC > 0 ? TMC : 4)], parked[(4 * it + 2) % (TMC > 0 ? TMC : 4)], parked[(4 * it + 3) % (TMC > 0 ? TMC : 4)])
+            if (TMC > 0 && it < TCH && it % 8 == 0) tmem_ld32(twarp + 4 * it, parked);
+            sq_fetch(it + SQD);
+            if (staged(it)) {
+                const float4 cs = (TMC > 0 && it < TCH) ? make_float4(parked[(4 * it) % 32], parked[(4 * it + 1) % 32], parked[(4 * it + 2) % 32], parked[(4 * it + 3) % 32])
                                                         : LDC(cs4 + it * THREADS);
+                float x0r, x1r;
                 if (TXF) {
-                    /* symbol index 2*b0 + b1 (first byte = MSB, digital/util.rs:5-11).  qpsk.rs:23-35 is odd in the pair of
-                     * signs, so entry 3 = -entry 0 and entry 2 = -entry 1 bit for bit (the launcher checks the table):
-                     * one select between entries 0 and 1, then the sign from b0 */
-                    const uint32_t w = sw[TXF ? it : 0];
-                    const bool mid = ((w ^ (w >> 8)) & 1u) != 0;
-                    const uint32_t sg = w << 31;
-                    const float si = __uint_as_float(__float_as_uint(mid ? t1.x : a.tx_iq[0].x) ^ sg);
-                    const float sq = __uint_as_float(__float_as_uint(mid ? t1.y : a.tx_iq[0].y) ^ sg);
-#if MG_TXF_PACKED_MIX
+                    const float2 sq = unpk2(sqv[TXF ? it : 0]); /* (i, q) of the chunk's symbol */
                     /* modulator.rs:37-43 on packed pairs: (i*c, i*s) and (q*s, q*c) by two FMUL2, then
                      * (i*c - q*s, i*s + q*c) by one FFMA2 with (-1, +1): a product by +-1 is exact, so the fma's one
                      * rounding is the rounding of the reference's subtraction / addition */
-                    const f32x2 ii = pk2(si, si), qq = pk2(sq, sq), pm = pk2(-1.0f, 1.0f);
-                    const float2 x0 = unpk2(fma2(mul2(qq, pk2(cs.y, cs.x)), pm, mul2(ii, pk2(cs.x, cs.y))));
-                    const float2 x1 = unpk2(fma2(mul2(qq, pk2(cs.w, cs.z)), pm, mul2(ii, pk2(cs.z, cs.w))));
-#else
-                    const float2 x0 = mix_iq(si, sq, cs.x, cs.y), x1 = mix_iq(si, sq, cs.z, cs.w);
-#endif
-                    /* this tile owns local samples >= 8*(NB-1) (what the previous tile did not reach) */
-                    const bool own = first_tile || it > 0 || tid >= 4 * (C::NB - 1);
-                    if (((vmask >> it) & 1ull) && own && a.tx_out) __stcs(txrow + it * THREADS, make_float4(x0.x, x0.y, x1.x, x1.y));
+                    const f32x2 ii = pk2(sq.x, sq.x), qq = pk2(sq.y, sq.y), pm = pk2(-1.0f, 1.0f);
+                    const f32x2 x0 = fma2(mul2(qq, pk2(cs.y, cs.x)), pm, mul2(ii, pk2(cs.x, cs.y)));
+                    const f32x2 x1 = fma2(mul2(qq, pk2(cs.w, cs.z)), pm, mul2(ii, pk2(cs.z, cs.w)));
+                    /* this tile owns local samples >= 8*(NB-1) (what the previous tile did not reach); outside the frame
+                     * (edge tiles) nothing is stored */
+                    const bool own = EDGE ? ((vmask >> it) & 1) != 0 && (first_tile || it > 0 || tid >= 4 * (C::NB - 1))
+                                          : (it > 0 || tid >= 4 * (C::NB - 1));
+                    if (own && store_tx) __stcs(reinterpret_cast<float4*>(txrow + it * THREADS), make_float4(unpk2(x0).x, unpk2(x0).y, unpk2(x1).x, unpk2(x1).y));
                     /* outside the frame the NCO table holds zeros: x is +-0 there, like the zero the unfused kernel stages */
-                    xr[it][0] = x0.x;
-                    xr[it][1] = x1.x;
+                    x0r = unpk2(x0).x;
+                    x1r = unpk2(x1).x;
+                } else {
+                    x0r = xr[it][0];
+                    x1r = xr[it][1];
                 }
-                /* demodulator.rs:53-54: x*cos, x*(-sin); chunk q = it*THREADS + tid sits at position
-                 * q + q/PADW = wbase + it*(THREADS + THREADS/PADW) */
+                /* demodulator.rs:53-54 stages x*cos and x*(-sin).  The Q rail is kept NEGATED here, (x*cos, x*sin): one
+                 * FMUL2 per sample with the NCO pair as it lies in the table (a lane-wise negation costs an extra
+                 * instruction per sample), and phase C takes 0 - acc.  Exact: round-to-nearest is symmetric, so every
+                 * product and every partial sum of the negated rail is the negation of the reference's, and a partial
+                 * sum that is zero is +0 in both (the fold starts from +0 and x + (-x) = +0), which 0 - acc restores.
+                 * chunk q = it*THREADS + tid sits at position q + q/PADW = wbase + it*(THREADS + THREADS/PADW) */
                 s_v[wbase + it * (THREADS + THREADS / C::PADW)] =
-                    make_float4(__fmul_rn(xr[it][0], cs.x), __fmul_rn(xr[it][0], -cs.y), __fmul_rn(xr[it][1], cs.z),
-                                __fmul_rn(xr[it][1], -cs.w));
+                    make_ulonglong2(mul2(pk2(x0r, x0r), pk2(cs.x, cs.y)), mul2(pk2(x1r, x1r), pk2(cs.z, cs.w)));
             }
         }
+    };
+    if (PF == 2 && f0 < f1 && !TXF) load_tile(frame, std::true_type{});
+    for (u64 f = f0; f < f1; ++f, orow += a.K, frame += a.L) {
+        __syncthreads(); /* previous frame's phase B finished; s_slut, s_sq visible */
+        if (edge) phase_a(frame, f, std::true_type{});
+        else phase_a(frame, f, std::false_type{});
         __syncthreads();
         if (TXF) {
             brow += a.ref_stride;
             txrow += a.L / 2;
             if (f + 1 < f1) fetch_bits(brow); /* the next frame's words fly during the FIR */
         }
-        if (PF == 2 && f + 1 < f1 && !TXF) load_tile(frame + a.L); /* next frame's loads fly during the FIR */
+        if (PF == 2 && f + 1 < f1 && !TXF) load_tile(frame + a.L, std::true_type{}); /* next frame's loads fly during the FIR */
         /* pull the next frame's tile towards L2 while the FIR runs: PF 1 = one prefetch per 128-byte
          * line through the LSU, PF 3 = one bulk (TMA) L2 prefetch of the whole tile by one thread */
         if (PF == 1 && f + 1 < f1 && !TXF) {
@@ -491,28 +530,32 @@ __global__ void __launch_bounds__(THREADS, MINB)
         for (int r = 0; r < R; ++r) {
             const float2 t = unpk2(acc[r]);
             ai[r] = t.x;
-            aq[r] = t.y;
+            aq[r] = __fsub_rn(0.0f, t.y); /* the Q rail was accumulated negated (phase A) */
         }
         /* ---- phase C */
         if (vec_out) {
-            uint32_t symw[2] = {0u, 0u}, bitw[4] = {0u, 0u, 0u, 0u}, nerr = 0;
+            uint32_t symw[2] = {0u, 0u}, bitw[4] = {0u, 0u, 0u, 0u};
+            float I[R], Q[R];
+            /* sign slicer (a.sign_slice: the launcher found the scaled table to be (-+A, -+B) in index order with
+             * A, B within a factor 2 of each other): b0 = I > 0, b1 = Q > 0 IS the nearest-point search with its binary32
+             * roundings and its tie rule whenever every |I|, |Q| of the thread lies in [ss_lo, ss_hi] = [min(A,B)/1024,
+             * 4 min(A,B)] -- the true distance gap 4|I|A >= 2^-8 min^2 then exceeds every rounding error of the search
+             * (< 2^-16 min^2) -- and anything else (tiny, huge, NaN) takes the search itself */
+            bool quick = a.sign_slice != 0;
 #pragma unroll
             for (int r = 0; r < R; ++r) {
-                const float I = __fmul_rn(a.rx_gain, ai[r]), Q = __fmul_rn(a.rx_gain, aq[r]);
-                const uint32_t s = lut4 ? slice_point_reg4(rl, I, Q) : slice_point4(s_slut + toff[r], a.n_const, I, Q);
+                I[r] = __fmul_rn(a.rx_gain, ai[r]);
+                Q[r] = __fmul_rn(a.rx_gain, aq[r]);
+                quick = quick && fabsf(I[r]) >= a.ss_lo && fabsf(I[r]) <= a.ss_hi && fabsf(Q[r]) >= a.ss_lo && fabsf(Q[r]) <= a.ss_hi;
+            }
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                uint32_t s;
+                if (quick) s = ((~__float_as_uint(I[r]) >> 31) << 1) | (~__float_as_uint(Q[r]) >> 31);
+                else s = lut4 ? slice_point_reg4(rl, I[r], Q[r]) : slice_point4(s_slut + toff[r], a.n_const, I[r], Q[r]);
                 symw[r / 4] |= s << (8 * (r % 4));
                 bitw[r / 2] |= ((s >> 1) | ((s & 1u) << 8)) << (16 * (r % 2));
-                if (a.soft) a.soft[orow + r] = make_float2(I, Q);
-                if (a.ref_bits) {
-                    uint32_t ref;
-                    if (ref_vec) {
-                        const uint32_t h = refw[r / 2] >> (16 * (r % 2));
-                        ref = ((h & 1u) << 1) | ((h >> 8) & 1u);
-                    } else {
-                        ref = pack_symbol(refp + 2 * r, 2);
-                    }
-                    nerr += __popc(ref ^ s);
-                }
+                if (a.soft) a.soft[orow + r] = make_float2(I[r], Q[r]);
             }
             if (a.sym) {
                 if (R == 8) *reinterpret_cast<uint2*>(a.sym + orow) = make_uint2(symw[0], symw[1]);
@@ -525,6 +568,17 @@ __global__ void __launch_bounds__(THREADS, MINB)
                 else *reinterpret_cast<uint32_t*>(a.bits + 2 * orow) = bitw[0];
             }
             if (a.ref_bits) {
+                uint32_t nerr = 0;
+                if (ref_vec) { /* bit bytes against bit bytes, four at a time (only bit 0 of a reference byte counts, as in pack_symbol) */
+#pragma unroll
+                    for (int j = 0; j < (R + 1) / 2; ++j) nerr += __popc((bitw[j] ^ refw[j]) & 0x01010101u);
+                } else {
+#pragma unroll
+                    for (int r = 0; r < R; ++r) {
+                        const uint32_t h = bitw[r / 2] >> (16 * (r % 2));
+                        nerr += __popc(pack_symbol(refp + 2 * r, 2) ^ (((h & 1u) << 1) | ((h >> 8) & 1u)));
+                    }
+                }
                 err += nerr;
                 cmp += 2 * R;
             }
@@ -556,21 +610,26 @@ cudaError_t rx_fast_launch_t(const RxArgs& a, const float* h_taps, cudaStream_t 
     const TapsParam<NT> tp = make_taps_param<NT>(h_taps);
     const size_t smem = C::smem(a.n_tables * a.n_const);
     auto kern = rx_fast_kernel<NT, OFF, FMA, NOISE, THREADS, MINB, R, PF, TMC, TXF>;
-    static size_t configured = 0; /* per instantiation: set the attributes once per shared-memory size */
-    if (configured != smem) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    /* the attributes are per DEVICE (and per instantiation): remember the shared-memory size each device was configured for */
+    static std::atomic<size_t> configured[kMaxDevices];
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev < 0 || dev >= kMaxDevices || configured[dev].load(std::memory_order_acquire) != smem + 1) {
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         if (e != cudaSuccess) return e;
-        configured = smem;
+        if (dev >= 0 && dev < kMaxDevices) configured[dev].store(smem + 1, std::memory_order_release);
     }
     kern<<<grid, THREADS, smem, stream>>>(a, tp);
     return cudaGetLastError();
 }
 
-/* all (OFF, FMA, NOISE) combinations of one (NT, THREADS, MINB) */
-template <int NT, int THREADS, int MINB, int R, int PF = RX_DEFAULT_PF, int TMC = RX_DEFAULT_TMC>
-cudaError_t rx_fast_dispatch(const RxArgs& a, const float* h_taps, bool fma, cudaStream_t stream)
+/* all (OFF, FMA, NOISE) combinations of one (NT, THREADS, MINB); tmem = false (MODEM_FLAG_NO_TMEM) selects the
+ * instantiation that keeps every NCO value in L1 and allocates no tensor memory */
+template <int NT, int THREADS, int MINB, int R, int PF, int TMC>
+cudaError_t rx_fast_dispatch_tmc(const RxArgs& a, const float* h_taps, bool fma, cudaStream_t stream)
 {
     const bool odd = (a.delay & 1u) != 0; /* OFF = 0 for odd delay, 1 for even */
     const bool noise = a.nz.sigma != 0.0f;
@@ -583,6 +642,12 @@ cudaError_t rx_fast_dispatch(const RxArgs& a, const float* h_taps, bool fma, cud
         else     { if (noise) MG_RX_CASE(1, false, true); else MG_RX_CASE(1, false, false); }
     }
 #undef MG_RX_CASE
+}
+template <int NT, int THREADS, int MINB, int R, int PF = RX_DEFAULT_PF, int TMC = RX_DEFAULT_TMC>
+cudaError_t rx_fast_dispatch(const RxArgs& a, const float* h_taps, bool fma, bool tmem, cudaStream_t stream)
+{
+    if (!tmem) return rx_fast_dispatch_tmc<NT, THREADS, MINB, R, PF, 0>(a, h_taps, fma, stream);
+    return rx_fast_dispatch_tmc<NT, THREADS, MINB, R, PF, TMC>(a, h_taps, fma, stream);
 }
 
 } /* namespace mg */

@@ -472,7 +472,11 @@ def _device_loopback(pkg, m, bits, want_sym=True, want_bits=True, want_tx=True):
             tuple(d_cnt.tolist()), m.launch_count - n0)
 
 
-@pytest.mark.parametrize("F,nsym", [(1, 8), (16, 2048), (6, 1064), (19, 8 * 37), (3, 300), (21, 1112), (9, 256 * 3 + 252), (21, 1111), (40, 2048 + 5), (9, 256 * 3 + 251), (5, 256 * 2 + 4)])
+FUSED_TS = 512  # symbols per tile of the fused loopback kernel (loop_fused_64.cu: 128 threads x 4 symbols)
+
+
+@pytest.mark.parametrize("F,nsym", [(1, 8), (16, 2048), (6, 1064), (19, 8 * 37), (3, 300), (21, 1112), (9, 256 * 3 + 252), (21, 1111), (40, 2048 + 5), (9, 256 * 3 + 251), (5, 256 * 2 + 4),
+                                    (7, 512 + 508), (5, 512 * 2 + 4), (3, 512 * 3), (4, 512 + 8)])
 def test_fused_loopback_matches_oracle_and_two_kernel_path(pkg, orc, F, nsym, monkeypatch):
     """The fused loopback kernel (TX samples made, stored and demodulated by one kernel) against the oracle and
     against the two-kernel path: TX buffer bit-identical and completely written (ragged tiles, frames that end inside
@@ -494,7 +498,7 @@ def test_fused_loopback_matches_oracle_and_two_kernel_path(pkg, orc, F, nsym, mo
     assert np.array_equal(sym, sym2) and np.array_equal(out, out2) and cnt == cnt2
     # two kernels when K = nsym - 4 fills its tiles exactly (the last tile stops 4 samples short of the frame's end)
     # or when the rows of bits (2 bytes per symbol) do not start on 8-byte boundaries
-    fallback = nsym % 256 == 4 or nsym % 4 != 0
+    fallback = nsym % FUSED_TS == 4 or nsym % 4 != 0
     assert launches2 == 3 and launches == (3 if fallback else 2), (launches, launches2)  # NCO table + kernels
 
 
@@ -514,6 +518,78 @@ def test_fused_loopback_is_one_kernel_and_optional_outputs(pkg, orc):
     # no TX buffer asked for: the samples never leave the chip, the decisions are the same
     tx4, sym4, out4, cnt4, launches4 = _device_loopback(pkg, m, bits, want_tx=False)
     assert tx4 is None and launches4 == 1 and np.array_equal(sym4, sym) and np.array_equal(out4, out) and cnt4 == cnt
+
+
+def test_fused_loopback_rotated_table_and_no_tmem(pkg, orc, monkeypatch):
+    """The fused kernel takes ANY one 4-point table (symbol pairs are looked up by index, not derived from a sign
+    symmetry): QPSK rotated by 0.3 rad has no axis-aligned slicer either, so this also exercises the nearest-point
+    search inside the fused kernel.  No oracle scheme name reaches that table, so the reference here is the two-kernel
+    GPU path (tx_rect_fast + rx_fast, each pinned to the oracle by the other tests).  MODEM_FLAG_NO_TMEM (no tensor
+    memory allocated) must not change a bit either."""
+    import ctypes as C
+
+    tab = np.zeros((4, 2), np.float32)
+    assert pkg.lib().modem_const_qpsk(C.c_float(0.3), C.c_float(1.0), tab.ctypes.data_as(C.POINTER(C.c_float))) == 2
+    kw = path_kwargs("qpsk", sps=8)
+    kw.pop("scheme")
+    bits = rand_bits(91, 11, 2 * 1300)
+    res = {}
+    for name, env, flags in (("fused", None, 0), ("fused, no tmem", None, pkg.FLAG_NO_TMEM), ("two kernels", "1", 0), ("two kernels, no tmem", "1", pkg.FLAG_NO_TMEM)):
+        if env:
+            monkeypatch.setenv("MODEM_GPU_NO_FUSED_LOOP", env)
+        m = pkg.Modem(const_iq=tab[None], bps=2, flags=flags, **kw)
+        res[name] = _device_loopback(pkg, m, bits)
+        m.close()
+    tx, sym, out, cnt, launches = res["fused"]
+    assert launches == 2 and res["two kernels"][4] == 3
+    assert cnt[0] == 0 and cnt[1] == out.size and np.array_equal(out, bits[:, : out.shape[1]])
+    for name, r in res.items():
+        assert np.array_equal(r[0].view(np.uint32), tx.view(np.uint32)), name
+        assert np.array_equal(r[1], sym) and np.array_equal(r[2], out) and r[3] == cnt, name
+    # the unrotated table through the same four forms, against the oracle
+    kw = path_kwargs("qpsk", sps=8)
+    o = orc.OraclePath(**kw)
+    tx_ref = o.modulate(bits)
+    sym_ref, bits_ref, cnt_ref = o.loopback(bits, threads=4)
+    monkeypatch.delenv("MODEM_GPU_NO_FUSED_LOOP")
+    for env, flags in ((None, pkg.FLAG_NO_TMEM), ("1", pkg.FLAG_NO_TMEM)):
+        if env:
+            monkeypatch.setenv("MODEM_GPU_NO_FUSED_LOOP", env)
+        m = pkg.Modem(flags=flags, **kw)
+        tx, sym, out, cnt, _ = _device_loopback(pkg, m, bits)
+        assert_buffers(tx, tx_ref, "no-tmem tx")
+        assert np.array_equal(sym, sym_ref) and np.array_equal(out, bits_ref) and cnt == cnt_ref
+
+
+def test_sign_slicer_equals_the_search(pkg, orc, monkeypatch):
+    """The QPSK sign slicer of the fast RX kernel (b0 = I > 0, b1 = Q > 0 inside a window of |I|, |Q|, the nearest-point
+    search outside it) must return the search's answer -- roundings and tie rule (lowest index) included -- for ANY
+    input: ordinary soft values, exact zeros (all four distances tie -> symbol 0), tiny values whose distance difference
+    is lost to rounding, huge values, infinities and NaNs."""
+    kw = path_kwargs("qpsk", sps=8)
+    m, o = make(pkg, orc, **kw)
+    rng = np.random.default_rng(5)
+    F, L = 12, 8 * 700
+    rx = rng.standard_normal((F, L, 2)).astype(np.float32)
+    rx[1] = 0.0                                             # exact zeros: ties
+    rx[2] *= np.float32(1e-9)                               # far below the window: search
+    rx[3] *= np.float32(1e-3)                               # around the window's lower edge
+    rx[4] *= np.float32(1e6)                                # above the window
+    rx[5, ::97, 0] = np.nan                                 # NaNs poison a filter span each
+    rx[6, ::131, 0] = np.inf
+    rx[7, ::89, 0] = -np.inf
+    rx[8] = np.float32(1e-41)                               # denormals
+    rx[9, :, 0] = np.where(np.arange(L) % 16 < 8, 1.0, -1.0).astype(np.float32) * np.float32(2.0 ** -11)  # I, Q near lo
+    rx[10] *= np.float32(1e30)                              # overflows to inf inside the FIR
+    with np.errstate(all="ignore"):
+        _, sym_ref, bits_ref = o.demodulate(rx, want_filt=False)
+    got = m.demodulate(rx)
+    assert np.array_equal(got["sym"], sym_ref) and np.array_equal(got["bits"], bits_ref)
+    assert len(np.unique(sym_ref[0])) == 4
+    monkeypatch.setenv("MODEM_GPU_NO_SIGN_SLICE", "1")
+    m2 = pkg.Modem(**kw)
+    got2 = m2.demodulate(rx)
+    assert np.array_equal(got2["sym"], sym_ref) and np.array_equal(got2["bits"], bits_ref)
 
 
 def test_fused_loopback_bank_and_fallbacks(pkg, orc):
