@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define MODEM_GPU_ABI_VERSION 2
+#define MODEM_GPU_ABI_VERSION 3
 
 enum {
     MODEM_OK = 0,
@@ -193,10 +193,17 @@ int modem_gpu_preamble(modem_ctx_t* ctx, size_t F, size_t n, float amplitude, mo
 int modem_gpu_modulate_real(modem_ctx_t* ctx, const uint8_t* bits, size_t F, size_t nbits, size_t preamble,
                             float preamble_amplitude, float* out);
 
-/* awgn (extension): buf[f][n] += sigma * N(0,1) per component, Philox4x32-10 keyed by `seed`,
- * counter = (n/2, global frame id frame0+f).  In place. */
+/* awgn (extension): buf[f][n] += sigma * N(0,1) per component.  Philox4x32-10 keyed by `seed`, one block per aligned quad
+ * of samples and per rail (counter = (n/4, rail in bit 63, global frame id frame0+f)), Box-Muller as an explicit
+ * sequence of correctly rounded binary32 operations: the definition is in oracle/modem_oracle.h ("AWGN") and is what a
+ * CPU reproduces bit for bit.  In place. */
 int modem_gpu_awgn(modem_ctx_t* ctx, modem_c32_t* buf, size_t F, size_t L, float sigma,
                    uint64_t seed, uint64_t frame0);
+
+/* random_bits (extension, BASELINE config 4 "bits from Philox too"): payload bits for F frames generated on the device,
+ * bits [F][nbits] one byte (0/1) per bit (host or device pointer); bit j of global frame frame0+f is bit j % 32 of word
+ * (j % 128) / 32 of the Philox4x32-10 block with key (seed lo, seed hi ^ 0x62697473), counter (j/128, frame id). */
+int modem_gpu_random_bits(modem_ctx_t* ctx, uint8_t* bits, size_t F, size_t nbits, uint64_t seed, uint64_t frame0);
 
 /* demodulate: rx [F][L] complex -> per frame K = modem_gpu_decided_symbols(L) decisions.
  *   Replaces Demodulator::next (demodulator.rs:44-55) with its two FIRFilter::add

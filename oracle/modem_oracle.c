@@ -649,35 +649,61 @@ void orc_philox4x32_10(const uint32_t ctr_in[4], const uint32_t key_in[2], uint3
     out[0] = c[0]; out[1] = c[1]; out[2] = c[2]; out[3] = c[3];
 }
 
-float orc_u01(uint32_t r)
-{
-    return (float)((double)r * 0x1p-32 + 0x1p-33);
-}
+/* the normal pair of modem_oracle.h "AWGN": every operation is one correctly rounded binary32 operation */
 void orc_box_muller(uint32_t r0, uint32_t r1, float* n0, float* n1)
 {
-    const float TWO_PI = ORC_PI * 2.0f;
-    float u1 = orc_u01(r0), u2 = orc_u01(r1);
-    float rad = sqrtf(-2.0f * logf(u1));
-    float theta = TWO_PI * u2;
-    *n0 = rad * cosf(theta);
-    *n1 = rad * sinf(theta);
+    static const float L[7] = {-0x1.00001cp-1f, 0x1.555802p-2f, -0x1.ffa938p-3f, 0x1.97ecccp-3f, -0x1.5e404cp-3f, 0x1.495358p-3f, -0x1.ab64d2p-4f};
+    static const float S[3] = {-0x1.555552p-3f, 0x1.110c2ap-7f, -0x1.9aca02p-13f};
+    static const float C[4] = {-0x1p-1f, 0x1.55554cp-5f, -0x1.6c0e0cp-10f, 0x1.9a6fd8p-16f};
+    const float LN2 = 0x1.62e43p-1f, ANG = 0x1.921fb6p-22f;
+    /* radius */
+    float u = ((float)(r0 >> 9) + 0.5f) * 0x1p-23f;
+    uint32_t ub;
+    memcpy(&ub, &u, 4);
+    uint32_t ix = ub - 0x3f3504f3u;
+    int32_t e = (int32_t)ix >> 23;
+    uint32_t mb = (ix & 0x007fffffu) + 0x3f3504f3u;
+    float m;
+    memcpy(&m, &mb, 4);
+    float f = m - 1.0f;
+    float q = L[6];
+    for (int k = 5; k >= 0; --k) q = fmaf(q, f, L[k]);
+    float lnm = f * fmaf(f, q, 1.0f);
+    float lnu = fmaf((float)e, LN2, lnm);
+    float rad = sqrtf(-2.0f * lnu);
+    /* angle */
+    uint32_t j = r1 >> 8, oct = j >> 21, k = j & 0x1fffffu;
+    if (oct & 1u) k = 0x200000u - k;
+    float x = (float)k * ANG;
+    float z = x * x;
+    float sn = fmaf(x * z, fmaf(fmaf(S[2], z, S[1]), z, S[0]), x);
+    float cs = fmaf(z, fmaf(fmaf(fmaf(C[3], z, C[2]), z, C[1]), z, C[0]), 1.0f);
+    if ((oct + 1u) & 2u) { /* octants 1, 2, 5, 6 */
+        float t = sn;
+        sn = cs;
+        cs = t;
+    }
+    if ((oct + 2u) & 4u) cs = -cs; /* octants 2..5 */
+    if (oct & 4u) sn = -sn;        /* octants 4..7 */
+    *n0 = rad * cs;
+    *n1 = rad * sn;
 }
 void orc_awgn_sample(uint64_t seed, uint64_t frame, uint64_t n, float sigma, float* re, float* im)
 {
-    uint64_t pair = n >> 1;
-    uint32_t ctr[4] = {(uint32_t)pair, (uint32_t)(pair >> 32), (uint32_t)frame, (uint32_t)(frame >> 32)};
+    uint64_t quad = n >> 2;
     uint32_t key[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)};
-    uint32_t r[4];
-    orc_philox4x32_10(ctr, key, r);
-    /* one Philox block serves the aligned sample pair (2m, 2m+1): words 0,1 -> one Box-Muller pair whose cosine
-     * branch is the REAL-part noise of sample 2m and whose sine branch that of sample 2m+1; words 2,3 likewise
-     * for the imaginary parts.  (The demodulator only reads real parts, demodulator.rs:45-48: this way one
-     * logarithm, one square root and one sincos cover two samples.) */
-    float a0, a1, b0, b1;
-    orc_box_muller(r[0], r[1], &a0, &a1);
-    orc_box_muller(r[2], r[3], &b0, &b1);
-    *re = *re + sigma * ((n & 1) ? a1 : a0);
-    *im = *im + sigma * ((n & 1) ? b1 : b0);
+    float nz[2];
+    for (uint32_t rail = 0; rail < 2; ++rail) {
+        uint32_t ctr[4] = {(uint32_t)quad, (uint32_t)(quad >> 32) | (rail << 31), (uint32_t)frame, (uint32_t)(frame >> 32)};
+        uint32_t r[4];
+        orc_philox4x32_10(ctr, key, r);
+        float a0, a1;
+        if (n & 2) orc_box_muller(r[2], r[3], &a0, &a1);
+        else orc_box_muller(r[0], r[1], &a0, &a1);
+        nz[rail] = (n & 1) ? a1 : a0;
+    }
+    *re = *re + sigma * nz[0];
+    *im = *im + sigma * nz[1];
 }
 void orc_awgn(float* buf, size_t F, size_t L, float sigma, uint64_t seed, uint64_t frame0)
 {
@@ -686,6 +712,19 @@ void orc_awgn(float* buf, size_t F, size_t L, float sigma, uint64_t seed, uint64
             float* s = buf + 2 * (f * L + n);
             orc_awgn_sample(seed, frame0 + f, n, sigma, &s[0], &s[1]);
         }
+}
+void orc_random_bits(uint8_t* bits, size_t F, size_t nbits, uint64_t seed, uint64_t frame0)
+{
+    uint32_t key[2] = {(uint32_t)seed, (uint32_t)(seed >> 32) ^ 0x62697473u};
+    for (size_t f = 0; f < F; ++f) {
+        uint64_t g = frame0 + f;
+        for (size_t b = 0; b * 128 < nbits; ++b) {
+            uint32_t ctr[4] = {(uint32_t)b, (uint32_t)((uint64_t)b >> 32), (uint32_t)g, (uint32_t)(g >> 32)};
+            uint32_t r[4];
+            orc_philox4x32_10(ctr, key, r);
+            for (size_t j = b * 128; j < nbits && j < (b + 1) * 128; ++j) bits[f * nbits + j] = (uint8_t)((r[(j % 128) / 32] >> (j % 32)) & 1u);
+        }
+    }
 }
 
 float orc_sigma_for_ebn0(const float* const_iq, size_t n_points, size_t bps, float slicer_gain,

@@ -182,16 +182,43 @@ void orc_rrc_taps(float* out, size_t span, size_t sps, double beta);
 /* Philox4x32-10 (Salmon et al., SC'11).  ctr/key/out are 4/2/4 words. */
 void orc_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
 
-/* u32 -> (0,1]: (float)((double)r * 2^-32 + 2^-33) */
-float orc_u01(uint32_t r);
-/* Box-Muller: n0 = r*cos(t), n1 = r*sin(t), r = sqrtf(-2*logf(u1)), t = 2pi*u2 */
+/* ---- AWGN (extension; nothing in the reference).  DEFINED here as an explicit sequence of IEEE binary32 operations --
+ * mul, add, fused multiply-add (fmaf), sqrtf, all correctly rounded, evaluated in the order written -- so that a CPU and
+ * a GPU produce the same bits without either having to imitate the other's math library (round 1 defined the noise through
+ * glibc's logf/sinf/cosf and paid a binary64 libm per sample on the device to stay bit-identical).
+ *
+ *   normal pair from two Philox words (r0, r1)                                     [orc_box_muller]
+ *     u  = ((float)(r0 >> 9) + 0.5f) * 2^-23           uniform on (0, 1), exact in binary32
+ *     ln u:  ix = bits(u) - 0x3f3504f3;  e = (int)ix >> 23;  m = float(bits = (ix & 0x7fffff) + 0x3f3504f3)
+ *            f = m - 1.0f                                in [sqrt(1/2) - 1, sqrt(2) - 1), exact
+ *            q = L6; q = fmaf(q, f, L5); ... q = fmaf(q, f, L0)
+ *            lnm = f * fmaf(f, q, 1.0f);   lnu = fmaf((float)e, LN2, lnm)
+ *     rad = sqrtf(-2.0f * lnu)
+ *     angle: j = r1 >> 8 (24 bits = fraction of a turn); oct = j >> 21; k = j & 0x1fffff; if (oct & 1) k = 0x200000 - k
+ *            x = (float)k * ANG                          in [0, pi/4]
+ *            z = x * x;  s = fmaf(x * z, fmaf(fmaf(S2, z, S1), z, S0), x);  c = fmaf(z, fmaf(fmaf(fmaf(C3, z, C2), z, C1), z, C0), 1.0f)
+ *            octants 1, 2, 5, 6 swap (s, c); the cosine is negated in octants 2..5, the sine in octants 4..7
+ *     n0 = rad * cos, n1 = rad * sin
+ *   constants (binary32, hexadecimal): L0..L6 = -0x1.00001cp-1, 0x1.555802p-2, -0x1.ffa938p-3, 0x1.97ecccp-3, -0x1.5e404cp-3,
+ *     0x1.495358p-3, -0x1.ab64d2p-4;  LN2 = 0x1.62e43p-1;  ANG = 0x1.921fb6p-22 (2 pi 2^-24);  S0..S2 = -0x1.555552p-3,
+ *     0x1.110c2ap-7, -0x1.9aca02p-13;  C0..C3 = -0x1p-1, 0x1.55554cp-5, -0x1.6c0e0cp-10, 0x1.9a6fd8p-16.
+ *     (|ln error| < 5e-7 relative, |sin, cos error| < 6e-8: the distribution is the algorithm's by definition; its
+ *     closeness to a Gaussian is what tests/test_oracle_kat.py and the BER-against-theory tests check.)
+ *
+ *   noise of sample n of global frame g, seed s                                    [orc_awgn_sample]
+ *     one Philox4x32-10 block per aligned QUAD of samples and per rail: key = (s lo, s hi), counter =
+ *     (n/4 lo, (n/4 hi) | rail << 31, g lo, g hi), rail 0 = real parts, rail 1 = imaginary parts.  Words (0,1) ->
+ *     normal pair for samples 4q, 4q+1; words (2,3) -> pair for samples 4q+2, 4q+3.  x.re += sigma * a, x.im += sigma * b
+ *     (a product and a sum, each rounded).  The demodulator reads real parts only (demodulator.rs:45-48), so a receiver
+ *     that adds the noise on the fly needs ONE block per four samples and wastes none of it.
+ */
 void orc_box_muller(uint32_t r0, uint32_t r1, float* n0, float* n1);
-/* complex AWGN for sample n of global frame `frame`:  counter = (n/2 lo, n/2 hi,
- * frame lo, frame hi), key = (seed lo, seed hi).  Words 0,1 -> Box-Muller (a0, a1): the real-part
- * noise of samples 2m and 2m+1; words 2,3 -> (b0, b1): their imaginary-part noise.
- * re += sigma*a[n&1], im += sigma*b[n&1]. */
 void orc_awgn_sample(uint64_t seed, uint64_t frame, uint64_t n, float sigma, float* re, float* im);
 void orc_awgn(float* buf /*[F][L][2]*/, size_t F, size_t L, float sigma, uint64_t seed, uint64_t frame0);
+
+/* ---- random payload bits (extension): bit j of global frame g = bit (j % 32) of word (j % 128) / 32 of the Philox4x32-10
+ * block with key = (s lo, s hi ^ 0x62697473) and counter = (j/128 lo, j/128 hi, g lo, g hi); one byte (0/1) per bit. */
+void orc_random_bits(uint8_t* bits /*[F][nbits]*/, size_t F, size_t nbits, uint64_t seed, uint64_t frame0);
 
 /* Es = mean |c|^2 of the scheme's constellation; sigma for a given Eb/N0 so that the
  * slicer sees the textbook SNR (DESIGN.md "AWGN scaling"). */

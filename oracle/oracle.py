@@ -125,9 +125,9 @@ def lib():
         L.orc_rrc_taps.argtypes = [f32p, sz, sz, C.c_double]
         u32p = C.POINTER(C.c_uint32)
         L.orc_philox4x32_10.argtypes = [u32p, u32p, u32p]
-        L.orc_u01.restype = f32; L.orc_u01.argtypes = [C.c_uint32]
         L.orc_box_muller.argtypes = [C.c_uint32, C.c_uint32, f32p, f32p]
         L.orc_awgn.argtypes = [f32p, sz, sz, f32, C.c_uint64, C.c_uint64]
+        L.orc_random_bits.argtypes = [u8p, sz, sz, C.c_uint64, C.c_uint64]
         L.orc_sigma_for_ebn0.restype = f32
         L.orc_sigma_for_ebn0.argtypes = [f32p, sz, sz, f32, f32, f32p, sz, C.c_double]
         PA = C.POINTER(Path)
@@ -171,6 +171,19 @@ def rrc_taps(span, sps, beta):
     out = np.empty(span * sps + 1, np.float32)
     lib().orc_rrc_taps(_f32p(out), span, sps, beta)
     return out
+
+
+def random_bits(F, nbits, seed, frame0=0):
+    """Philox payload bits (extension, modem_oracle.h): [F][nbits] bytes 0/1."""
+    out = np.zeros((F, nbits), np.uint8)
+    lib().orc_random_bits(_u8p(out), F, nbits, seed, frame0)
+    return out
+
+
+def box_muller(r0, r1):
+    a, b = C.c_float(), C.c_float()
+    lib().orc_box_muller(r0, r1, C.byref(a), C.byref(b))
+    return a.value, b.value
 
 
 def philox4x32_10(ctr, key):

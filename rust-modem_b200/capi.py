@@ -106,6 +106,7 @@ def lib():
     L.modem_gpu_decided_symbols.restype = sz; L.modem_gpu_decided_symbols.argtypes = [vp, sz]
     L.modem_gpu_modulate.argtypes = [vp, u8p, sz, sz, vp, vp]
     L.modem_gpu_awgn.argtypes = [vp, vp, sz, sz, f32, u64, u64]
+    L.modem_gpu_random_bits.argtypes = [vp, vp, sz, sz, u64, u64]
     L.modem_gpu_demodulate.argtypes = [vp, vp, sz, sz, vp, vp, vp, vp, f32, u64, u64]
     L.modem_gpu_demodulate_count.argtypes = [vp, vp, sz, sz, vp, vp, vp, sz, vp, f32, u64, u64]
     L.modem_gpu_ber_sweep.argtypes = [vp, vp, sz, sz, sz, f32p, u64, u64, vp, vp]
@@ -294,6 +295,15 @@ class Modem:
     # -- raw-pointer entry points (numpy host arrays or torch tensors)
     def modulate_into(self, bits, F, nbits, tx=None, iq=None):
         self._ck(lib().modem_gpu_modulate(self._ctx, _ptr(bits), F, nbits, _ptr(tx), _ptr(iq)))
+
+    def random_bits_into(self, bits, F, nbits, seed, frame0=0):
+        """Philox payload bits generated on the device (host or device destination)."""
+        self._ck(lib().modem_gpu_random_bits(self._ctx, _ptr(bits), F, nbits, seed, frame0))
+
+    def random_bits(self, F, nbits, seed, frame0=0):
+        out = np.zeros((F, nbits), np.uint8)
+        self.random_bits_into(out, F, nbits, seed, frame0)
+        return out
 
     def awgn_inplace(self, buf, F, L, sigma, seed, frame0=0):
         self._ck(lib().modem_gpu_awgn(self._ctx, _ptr(buf), F, L, sigma, seed, frame0))

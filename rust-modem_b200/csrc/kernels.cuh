@@ -185,29 +185,64 @@ __global__ void __launch_bounds__(kThreads)
 }
 
 /* ================================================================== AWGN ========== */
-/* In place: buf[f][n] += sigma * (n0 + j n1).  One thread = one Philox call = 2 samples. */
+/* In place: buf[f][n] += sigma * (a + j b).  One thread = one quad of samples = two Philox blocks (real, imaginary rail). */
 __global__ void __launch_bounds__(kThreads) awgn_kernel(float2* buf, u64 F, u64 L, Noise nz)
 {
-    const u64 pairs_per_frame = (L + 1) / 2;
-    const u64 total = F * pairs_per_frame;
+    const u64 quads_per_frame = (L + 3) / 4;
+    const u64 total = F * quads_per_frame;
     for (u64 g = (u64)blockIdx.x * kThreads + threadIdx.x; g < total; g += (u64)gridDim.x * kThreads) {
-        const u64 f = g / pairs_per_frame, pair = g % pairs_per_frame;
+        const u64 f = g / quads_per_frame, quad = g % quads_per_frame;
         const u64 gf = nz.frame0 + f;
-        uint32_t r[4];
-        philox4x32_10((uint32_t)pair, (uint32_t)(pair >> 32), (uint32_t)gf, (uint32_t)(gf >> 32),
-                      (uint32_t)nz.seed, (uint32_t)(nz.seed >> 32), r);
-        float a[2], b[2];
-        box_muller(r[0], r[1], &a[0], &a[1]); /* real parts of samples 2m, 2m+1 */
-        box_muller(r[2], r[3], &b[0], &b[1]); /* imaginary parts */
+        uint32_t ra[4], rb[4];
+        noise_quad(nz, gf, quad, 0, ra);
+        noise_quad(nz, gf, quad, 1, rb);
+        float a[4], b[4];
+        box_muller(ra[0], ra[1], &a[0], &a[1]);
+        box_muller(ra[2], ra[3], &a[2], &a[3]);
+        box_muller(rb[0], rb[1], &b[0], &b[1]);
+        box_muller(rb[2], rb[3], &b[2], &b[3]);
 #pragma unroll
-        for (int e = 0; e < 2; ++e) {
-            const u64 n = pair * 2 + e;
+        for (int e = 0; e < 4; ++e) {
+            const u64 n = quad * 4 + e;
             if (n >= L) break;
             float2* p = buf + f * L + n;
             float2 v = *p;
             v.x = __fadd_rn(v.x, __fmul_rn(nz.sigma, a[e]));
             v.y = __fadd_rn(v.y, __fmul_rn(nz.sigma, b[e]));
             *p = v;
+        }
+    }
+}
+
+/* Payload bits from Philox (extension, oracle/modem_oracle.h "random payload bits"): one thread = one block = 128 bits */
+__global__ void __launch_bounds__(kThreads) random_bits_kernel(uint8_t* bits, u64 F, u64 nbits, u64 seed, u64 frame0)
+{
+    const u64 blocks_per_frame = (nbits + 127) / 128;
+    const u64 total = F * blocks_per_frame;
+    const bool vec = (nbits % 16 == 0) && ((reinterpret_cast<uintptr_t>(bits) & 15u) == 0);
+    for (u64 g = (u64)blockIdx.x * kThreads + threadIdx.x; g < total; g += (u64)gridDim.x * kThreads) {
+        const u64 f = g / blocks_per_frame, b = g % blocks_per_frame;
+        const u64 gf = frame0 + f;
+        uint32_t r[4];
+        philox4x32_10((uint32_t)b, (uint32_t)(b >> 32), (uint32_t)gf, (uint32_t)(gf >> 32), (uint32_t)seed,
+                      (uint32_t)(seed >> 32) ^ 0x62697473u, r);
+        uint8_t* row = bits + f * nbits + b * 128;
+        const u64 left = nbits - b * 128;
+        if (vec && left >= 128) {
+#pragma unroll
+            for (int w = 0; w < 4; ++w)
+#pragma unroll
+                for (int h = 0; h < 2; ++h) { /* 16 bits -> 16 bytes */
+                    uint32_t o[4];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const uint32_t nib = (r[w] >> (16 * h + 4 * k)) & 0xfu;
+                        o[k] = (nib & 1u) | ((nib & 2u) << 7) | ((nib & 4u) << 14) | ((nib & 8u) << 21);
+                    }
+                    reinterpret_cast<uint4*>(row)[2 * w + h] = make_uint4(o[0], o[1], o[2], o[3]);
+                }
+        } else {
+            for (u64 j = 0; j < left && j < 128; ++j) row[j] = (uint8_t)((r[j / 32] >> (j % 32)) & 1u);
         }
     }
 }

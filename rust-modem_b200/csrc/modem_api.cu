@@ -73,12 +73,9 @@ struct modem_ctx {
         cudaStream_t s = nullptr;
         cudaEvent_t done = nullptr;
     } lanes[3];
-    static constexpr int kPipeSlots = 4;
-    struct Slot {
-        cudaEvent_t in_done = nullptr, comp_done = nullptr, out_done = nullptr;
-        Scratch bits, sym, out;
-    } slots[kPipeSlots];
-    Scratch pipe_tx;
+    std::vector<cudaEvent_t> pipe_events; /* 3 per chunk: copied in, computed, copied out (the last only when tracing) */
+    cudaEvent_t pipe_t0 = nullptr;
+    Scratch pipe_tx; /* one chunk of TX samples (two-kernel form only) */
     bool lanes_ready = false;
     cudaEvent_t ev_start = nullptr;
     u64 frame_base = 0; /* see ChannelView::frame_base */
@@ -104,7 +101,9 @@ struct modem_ctx {
     bool use_graph = true; /* MODEM_GPU_NO_GRAPH=1 disables */
     uint64_t launches = 0;
     bool force_generic = false;
-    bool pipe_fused = false; /* MODEM_GPU_PIPE_FUSED=1: the host-buffer pipeline uses the fused loopback kernel too */
+    bool pipe_trace = false; /* MODEM_GPU_PIPE_TRACE=1: per-chunk event timeline of the host-buffer pipeline on stderr */
+    bool pipe_fused = false; /* MODEM_GPU_PIPE_FUSED=1: the host-buffer pipeline runs the fused loopback kernel per chunk instead of TX + RX (measured slower, see loopback_pipelined) */
+    bool pipe_ramp = false; /* MODEM_GPU_PIPE_RAMP=1: short chunks at both ends of the call (measured slower with TX + RX, a wash with the fused kernel) */
     bool no_sign_slice = false; /* MODEM_GPU_NO_SIGN_SLICE=1: the fast RX kernel always runs the nearest-point search */
     bool no_fused_loop = false; /* MODEM_GPU_NO_FUSED_LOOP=1: the loopback entries run the TX and the RX kernel separately */
     int rx_fpb = 0, rx_tile_major = -1; /* MODEM_GPU_RX_FPB / MODEM_GPU_RX_TILEMAJOR: tuning knobs */
@@ -846,6 +845,10 @@ int modem_gpu_create(modem_ctx_t** out, int device, const modem_cfg_t* cfg)
     ctx->force_generic = fg && fg[0] == '1';
     const char* pf = getenv("MODEM_GPU_PIPE_FUSED");
     ctx->pipe_fused = pf && pf[0] == '1';
+    const char* pr = getenv("MODEM_GPU_PIPE_RAMP");
+    ctx->pipe_ramp = pr && pr[0] == '1';
+    const char* ptr = getenv("MODEM_GPU_PIPE_TRACE");
+    ctx->pipe_trace = ptr && ptr[0] == '1';
     const char* nf = getenv("MODEM_GPU_NO_FUSED_LOOP");
     ctx->no_fused_loop = nf && nf[0] == '1';
     const char* nss = getenv("MODEM_GPU_NO_SIGN_SLICE");
@@ -900,12 +903,9 @@ void modem_gpu_destroy(modem_ctx_t* ctx)
         if (ln.done) cudaEventDestroy(ln.done);
         if (ln.s) cudaStreamDestroy(ln.s);
     }
-    for (auto& sl : ctx->slots) {
-        for (void* p : {sl.bits.p, sl.sym.p, sl.out.p})
-            if (p) cudaFree(p);
-        for (cudaEvent_t e : {sl.in_done, sl.comp_done, sl.out_done})
-            if (e) cudaEventDestroy(e);
-    }
+    for (cudaEvent_t e : ctx->pipe_events)
+        if (e) cudaEventDestroy(e);
+    if (ctx->pipe_t0) cudaEventDestroy(ctx->pipe_t0);
     if (ctx->pipe_tx.p) cudaFree(ctx->pipe_tx.p);
     if (ctx->ev_start) cudaEventDestroy(ctx->ev_start);
     for (auto e : ctx->ev_pool)
@@ -1154,8 +1154,8 @@ int modem_gpu_awgn(modem_ctx_t* ctx, modem_c32_t* buf, size_t F, size_t L, float
         CK(ctx, cudaMemcpyAsync(d, buf, bytes, cudaMemcpyHostToDevice, ctx->stream));
     }
     mg::Noise nz{sigma, seed, frame0};
-    const u64 pairs = (u64)F * ((L + 1) / 2);
-    const unsigned blocks = (unsigned)std::min<u64>((pairs + mg::kThreads - 1) / mg::kThreads, (u64)ctx->sm_count * 32);
+    const u64 quads = (u64)F * ((L + 3) / 4);
+    const unsigned blocks = (unsigned)std::min<u64>((quads + mg::kThreads - 1) / mg::kThreads, (u64)ctx->sm_count * 32);
     mg::awgn_kernel<<<blocks, mg::kThreads, 0, ctx->stream>>>(d, F, L, nz);
     ctx->launches++;
     CK(ctx, cudaGetLastError());
@@ -1164,6 +1164,24 @@ int modem_gpu_awgn(modem_ctx_t* ctx, modem_c32_t* buf, size_t F, size_t L, float
         CK(ctx, cudaStreamSynchronize(ctx->stream));
     }
     return MODEM_OK;
+}
+
+int modem_gpu_random_bits(modem_ctx_t* ctx, uint8_t* bits, size_t F, size_t nbits, uint64_t seed, uint64_t frame0)
+{
+    if (!ctx || (!bits && F && nbits)) return fail(ctx, MODEM_ERR_INVALID, "random_bits: null argument");
+    CK(ctx, cudaSetDevice(ctx->device));
+    if (F == 0 || nbits == 0) return MODEM_OK;
+    Staged sb;
+    int rc = stage_out(ctx, ctx->s_bits, bits, F * nbits, &sb);
+    if (rc) return rc;
+    const u64 total = (u64)F * ((nbits + 127) / 128);
+    const unsigned blocks = (unsigned)std::min<u64>((total + mg::kThreads - 1) / mg::kThreads, (u64)ctx->sm_count * 32);
+    mg::random_bits_kernel<<<blocks, mg::kThreads, 0, ctx->stream>>>((uint8_t*)sb.dev, F, nbits, seed, frame0);
+    ctx->launches++;
+    CK(ctx, cudaGetLastError());
+    rc = finish_out(ctx, sb);
+    if (!rc && sb.host) CK(ctx, cudaStreamSynchronize(ctx->stream));
+    return rc;
 }
 
 int modem_gpu_demodulate(modem_ctx_t* ctx, const modem_c32_t* rx, size_t F, size_t L, uint8_t* sym, uint8_t* bits,
@@ -1213,13 +1231,23 @@ int modem_gpu_demodulate_count(modem_ctx_t* ctx, const modem_c32_t* rx, size_t F
 
 namespace {
 /*
- * Host-buffer loopback, pipelined by role: lanes[0] issues every H2D(bits) back to back, lanes[1] runs
- * TX kernel -> RX kernel chunk after chunk, lanes[2] issues every D2H(sym, bits); events hand a chunk from one
- * stream to the next and return its slot of the ring when the consumer is done.  The H2D engine is the
- * bottleneck of the step (as many bytes come back as go in, on the other DMA direction), and in this form it
- * never waits for a chunk's kernels or its copy-out (the earlier lane-per-chunk form serialised
- * H2D -> kernels -> D2H inside a lane and left the engine idle whenever a lane was late).  Chunks carry
- * ~128 MB of TX samples (256 frames at 65536 samples): smaller chunks make the per-chunk kernels inefficient.
+ * Host-buffer loopback, pipelined by role: lanes[0] issues every H2D(bits) back to back, lanes[1] runs the kernels chunk
+ * after chunk, lanes[2] issues every D2H(sym, bits); one event per chunk and stage hands it to the next stream.  The
+ * call's bits and results live in WHOLE-CALL device buffers (64 + 96 MiB at C2: nothing next to 180 GB of HBM), so no
+ * stream ever waits for a buffer to be recycled (round 1 used a ring of 4 chunk slots).  The step moves as many bytes in
+ * as out and is bound by the two DMA directions running at once: 1.65 ms at C2 against 1.54 ms for the bare copies in the
+ * same 16 + 16 transfers (tools/pcie_floor.py).
+ *
+ * Each chunk runs TX kernel + RX kernel through a chunk-sized sample buffer, NOT the fused loopback kernel, although that
+ * one is cheaper (44 us against 72 us per 256-frame chunk, and no sample traffic at all): with it the step takes 2.13 ms.
+ * Measured (profiles/r02_e2e_pipeline.txt): the per-chunk event trace shows every 4 MiB copy, in both directions, taking
+ * ~140 us beside the fused kernel and ~93 us (its stand-alone time) beside TX + RX; SM clocks, P-state and link speed are
+ * identical; chunk size, chunk ramps, the fused kernel's CTA shape, tensor memory on or off and storing the samples after
+ * all change nothing; a device-to-device copy stream running BESIDE the fused pipeline brings it to 1.85 ms.  So the
+ * copy engines move data faster while the device memory is kept busy with reads and writes (the TX + RX form streams
+ * 4 GB through HBM per step, the fused form nothing) -- a property of the memory system's idle behaviour, not of the
+ * kernels -- and the form that is cheaper on the SMs loses on the step.  MODEM_GPU_PIPE_FUSED=1 selects it anyway;
+ * MODEM_GPU_PIPE_RAMP=1 adds short chunks at both ends of the call (slower with TX + RX, a wash with the fused kernel).
  */
 int loopback_pipelined(modem_ctx* ctx, const uint8_t* bits, size_t F, size_t nbits, float sigma, uint64_t seed,
                        uint64_t frame0, uint8_t* sym, uint8_t* bits_out, uint64_t counters[2], size_t Fc)
@@ -1235,9 +1263,35 @@ int loopback_pipelined(modem_ctx* ctx, const uint8_t* bits, size_t F, size_t nbi
         CK(ctx, cudaEventCreateWithFlags(&ctx->ev_start, cudaEventDisableTiming));
         ctx->lanes_ready = true;
     }
-    for (auto& sl : ctx->slots)
-        for (cudaEvent_t* e : {&sl.in_done, &sl.comp_done, &sl.out_done})
-            if (!*e) CK(ctx, cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+    /* chunk schedule: [fs, fs + n) */
+    std::vector<std::pair<size_t, size_t>> chunks;
+    {
+        const size_t unit = ctx->n_channels ? std::min(Fc, ctx->frames_per_channel) : 1; /* chunk edges stay on what Fc was aligned to */
+        std::vector<size_t> head;
+        if (ctx->pipe_ramp && !ctx->n_channels)
+            for (size_t n = std::max<size_t>(Fc / 8, 16); n < Fc; n *= 2) head.push_back(n);
+        size_t ramp = 0;
+        for (size_t n : head) ramp += n;
+        if (2 * ramp + Fc > F) head.clear(), ramp = 0;
+        size_t fs = 0;
+        for (size_t n : head) chunks.push_back({fs, n}), fs += n;
+        const size_t mid_end = F - ramp;
+        while (fs < mid_end) {
+            size_t n = std::min(Fc, mid_end - fs);
+            if (mid_end - fs - n < Fc / 2 && mid_end - fs - n > 0) n = mid_end - fs; /* no runt chunk before the down-ramp */
+            chunks.push_back({fs, n});
+            fs += n;
+        }
+        for (size_t i = head.size(); i-- > 0;) chunks.push_back({fs, head[i]}), fs += head[i];
+        (void)unit;
+    }
+    size_t max_n = 0;
+    for (auto& c : chunks) max_n = std::max(max_n, c.second);
+    while (ctx->pipe_events.size() < 3 * chunks.size()) {
+        cudaEvent_t e;
+        CK(ctx, cudaEventCreateWithFlags(&e, ctx->pipe_trace ? cudaEventDefault : cudaEventDisableTiming));
+        ctx->pipe_events.push_back(e);
+    }
     CK(ctx, cudaMemsetAsync(ctx->d_counters, 0, 2 * sizeof(u64), ctx->stream));
     {
         /* NCO tables for the whole call, built once before the streams fork (every chunk shares them) */
@@ -1245,63 +1299,64 @@ int loopback_pipelined(modem_ctx* ctx, const uint8_t* bits, size_t F, size_t nbi
         int rc0 = attach_carrier_table(ctx, dummy, F, L, false);
         if (rc0) return rc0;
     }
-    int rc = ensure(ctx, ctx->pipe_tx, Fc * L * sizeof(float2));
-    for (auto& sl : ctx->slots) {
-        if (!rc) rc = ensure(ctx, sl.bits, Fc * nbits);
-        if (!rc && sym) rc = ensure(ctx, sl.sym, Fc * K);
-        if (!rc && bits_out) rc = ensure(ctx, sl.out, Fc * K * bps);
-    }
+    /* which kernels: the fused loopback kernel (no sample buffer at all) when the shape allows, else TX + RX per chunk */
+    mg::RxArgs probe{};
+    ctx->frame_base = 0;
+    const bool fused = ctx->pipe_fused &&
+                       loop_fused_eligible(ctx, reinterpret_cast<const uint8_t*>(uintptr_t(16)), max_n, nbits, nullptr, sigma, probe);
+    int rc = ensure(ctx, ctx->s_bits, F * nbits);
+    if (!rc && sym) rc = ensure(ctx, ctx->s_sym, F * K);
+    if (!rc && bits_out) rc = ensure(ctx, ctx->s_bits_out, F * K * bps);
+    if (!rc && !fused) rc = ensure(ctx, ctx->pipe_tx, max_n * L * sizeof(float2));
     if (rc) return rc;
+    uint8_t* d_bits = (uint8_t*)ctx->s_bits.p;
+    uint8_t* d_sym = sym ? (uint8_t*)ctx->s_sym.p : nullptr;
+    uint8_t* d_out = bits_out ? (uint8_t*)ctx->s_bits_out.p : nullptr;
     CK(ctx, cudaEventRecord(ctx->ev_start, ctx->stream));
     for (auto& ln : ctx->lanes) CK(ctx, cudaStreamWaitEvent(ln.s, ctx->ev_start, 0));
 
     cudaStream_t user_stream = ctx->stream;
     cudaStream_t s_in = ctx->lanes[0].s, s_k = ctx->lanes[1].s, s_out = ctx->lanes[2].s;
+    /* MODEM_GPU_PIPE_TRACE=1: the pipeline's own events are created with timing and their times printed after the call
+     * (no extra events: extra records on three streams changed what they were meant to show) */
+    if (ctx->pipe_trace) {
+        if (!ctx->pipe_t0) CK(ctx, cudaEventCreate(&ctx->pipe_t0));
+        CK(ctx, cudaEventRecord(ctx->pipe_t0, user_stream)); /* time zero */
+    }
     const bool copies_out = K && (sym || bits_out);
     cudaError_t e = cudaSuccess;
-    /* equal chunks: a ramped schedule (quarter and half chunks at both ends, to shorten the one copy-in and the
-     * one copy-out nothing overlaps) measured 1.667 ms against 1.641 ms -- the short kernels cost more than they save */
-    size_t c = 0;
-    for (size_t fs = 0; fs < F && !rc && e == cudaSuccess; fs += Fc, ++c) {
-        const size_t n = std::min(Fc, F - fs);
-        auto& sl = ctx->slots[c % modem_ctx::kPipeSlots];
-        const bool reused = c >= (size_t)modem_ctx::kPipeSlots;
-        /* copy in: the slot's bits are free once the RX kernel of its previous chunk has compared against them */
-        if (reused) e = cudaStreamWaitEvent(s_in, sl.comp_done, 0);
-        if (e == cudaSuccess) e = cudaMemcpyAsync(sl.bits.p, bits + fs * nbits, n * nbits, cudaMemcpyHostToDevice, s_in);
-        if (e == cudaSuccess) e = cudaEventRecord(sl.in_done, s_in);
-        /* kernels: need this chunk's bits, and the slot's result buffers back from the previous copy-out */
-        if (e == cudaSuccess) e = cudaStreamWaitEvent(s_k, sl.in_done, 0);
-        if (e == cudaSuccess && reused && copies_out) e = cudaStreamWaitEvent(s_k, sl.out_done, 0);
+    /* every copy-in is enqueued first: the engine runs them back to back whatever the kernels do */
+    for (size_t c = 0; c < chunks.size() && e == cudaSuccess; ++c) {
+        const size_t fs = chunks[c].first, n = chunks[c].second;
+        e = cudaMemcpyAsync(d_bits + fs * nbits, bits + fs * nbits, n * nbits, cudaMemcpyHostToDevice, s_in);
+        if (e == cudaSuccess) e = cudaEventRecord(ctx->pipe_events[3 * c], s_in);
+    }
+    for (size_t c = 0; c < chunks.size() && !rc && e == cudaSuccess; ++c) {
+        const size_t fs = chunks[c].first, n = chunks[c].second;
+        e = cudaStreamWaitEvent(s_k, ctx->pipe_events[3 * c], 0);
         if (e != cudaSuccess) break;
         ctx->stream = s_k; /* launch_* enqueue on ctx->stream */
         ctx->frame_base = fs;
-        /* two kernels per chunk here: the fused loopback kernel (launch_loop_fused) measured SLOWER in this pipeline
-         * (2.1 ms against 1.65 ms per step, with or without storing the samples) whenever the copy-out of the previous
-         * chunk runs beside it; with the copy-out off both forms take 1.37 ms (tools/gpu_e2e_probe2.py) */
-        bool fused = false;
-        if (ctx->pipe_fused) { /* MODEM_GPU_PIPE_FUSED=1: tuning knob, see above */
-            rc = launch_loop_fused(ctx, (const uint8_t*)sl.bits.p, n, nbits, nullptr, sym ? (uint8_t*)sl.sym.p : nullptr,
-                                   bits_out ? (uint8_t*)sl.out.p : nullptr, ctx->d_counters, sigma);
-            fused = rc == 1;
-            if (fused) rc = MODEM_OK;
+        if (fused) {
+            rc = launch_loop_fused(ctx, d_bits + fs * nbits, n, nbits, nullptr, d_sym ? d_sym + fs * K : nullptr,
+                                   d_out ? d_out + fs * K * bps : nullptr, ctx->d_counters, sigma);
+            rc = rc == 1 ? MODEM_OK : (rc == 0 ? fail(ctx, MODEM_ERR_UNSUPPORTED, "loopback pipeline: internal: chunk not eligible for the fused kernel") : rc);
+        } else {
+            rc = launch_tx(ctx, d_bits + fs * nbits, n, nbits, (float2*)ctx->pipe_tx.p, nullptr);
+            if (!rc)
+                rc = launch_rx(ctx, (const float2*)ctx->pipe_tx.p, n, L, d_sym ? d_sym + fs * K : nullptr, d_out ? d_out + fs * K * bps : nullptr,
+                               nullptr, nullptr, d_bits + fs * nbits, nbits, ctx->d_counters, sigma, seed, frame0 + fs);
         }
-        if (!rc && !fused) rc = launch_tx(ctx, (const uint8_t*)sl.bits.p, n, nbits, (float2*)ctx->pipe_tx.p, nullptr);
-        if (!rc && !fused)
-            rc = launch_rx(ctx, (const float2*)ctx->pipe_tx.p, n, L, sym ? (uint8_t*)sl.sym.p : nullptr,
-                           bits_out ? (uint8_t*)sl.out.p : nullptr, nullptr, nullptr, (const uint8_t*)sl.bits.p, nbits,
-                           ctx->d_counters, sigma, seed, frame0 + fs);
         ctx->stream = user_stream;
         ctx->frame_base = 0;
         if (rc) break;
-        e = cudaEventRecord(sl.comp_done, s_k);
-        /* copy out */
+        e = cudaEventRecord(ctx->pipe_events[3 * c + 1], s_k);
         if (e == cudaSuccess && copies_out) {
-            e = cudaStreamWaitEvent(s_out, sl.comp_done, 0);
-            if (e == cudaSuccess && sym) e = cudaMemcpyAsync(sym + fs * K, sl.sym.p, n * K, cudaMemcpyDeviceToHost, s_out);
+            e = cudaStreamWaitEvent(s_out, ctx->pipe_events[3 * c + 1], 0);
+            if (e == cudaSuccess && sym) e = cudaMemcpyAsync(sym + fs * K, d_sym + fs * K, n * K, cudaMemcpyDeviceToHost, s_out);
             if (e == cudaSuccess && bits_out)
-                e = cudaMemcpyAsync(bits_out + fs * K * bps, sl.out.p, n * K * bps, cudaMemcpyDeviceToHost, s_out);
-            if (e == cudaSuccess) e = cudaEventRecord(sl.out_done, s_out);
+                e = cudaMemcpyAsync(bits_out + fs * K * bps, d_out + fs * K * bps, n * K * bps, cudaMemcpyDeviceToHost, s_out);
+            if (e == cudaSuccess && ctx->pipe_trace) e = cudaEventRecord(ctx->pipe_events[3 * c + 2], s_out);
         }
     }
     if (e != cudaSuccess && !rc) rc = fail(ctx, MODEM_ERR_CUDA, std::string("loopback pipeline: ") + cudaGetErrorString(e));
@@ -1318,6 +1373,14 @@ int loopback_pipelined(modem_ctx* ctx, const uint8_t* bits, size_t F, size_t nbi
     u64 h[2] = {0, 0};
     CK(ctx, cudaMemcpyAsync(h, ctx->d_counters, sizeof h, cudaMemcpyDeviceToHost, user_stream));
     CK(ctx, cudaStreamSynchronize(user_stream));
+    if (ctx->pipe_trace) {
+        fprintf(stderr, "pipe trace (us from call start, %s): chunk frames  copied-in  computed  copied-out\n", fused ? "fused kernel" : "two kernels");
+        for (size_t c = 0; c < chunks.size(); ++c) {
+            float t[3] = {0, 0, 0};
+            for (int j = 0; j < (copies_out ? 3 : 2); ++j) cudaEventElapsedTime(&t[j], ctx->pipe_t0, ctx->pipe_events[3 * c + j]);
+            fprintf(stderr, "  %3zu %5zu  %8.1f %8.1f %8.1f\n", c, chunks[c].second, t[0] * 1e3, t[1] * 1e3, t[2] * 1e3);
+        }
+    }
     if (counters) {
         counters[0] += h[0];
         counters[1] += h[1];

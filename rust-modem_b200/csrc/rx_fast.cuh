@@ -295,32 +295,22 @@ __global__ void __launch_bounds__(THREADS, MINB)
      * arithmetic.  (Round 1: 2-byte loads and select/sign logic per CHUNK, 8 instructions x 17 chunks per thread and
      * frame.)  Rows start on 8-byte boundaries (the launcher checks). */
     constexpr int BWORDS = (2 * C::NBLK + 7 + 7) / 8;
-    constexpr int WPT = (BWORDS + THREADS - 1) / THREADS; /* words per thread: 2 (3 at R = 8) */
+    static_assert(!TXF || BWORDS <= 2 * THREADS, "two words per thread at most");
     __shared__ __align__(16) f32x2 s_sq[TXF ? 4 * BWORDS : 2];
     const long long brow0 = (2 * (nbase >> 3)) & ~7ll; /* row byte offset of table entry 0; negative in the first tile */
     /* this thread's first chunk lies in symbol (nbase + 2*tid) >> 3; chunk it*THREADS + tid: THREADS/4 symbols on per step */
     const int sqoff = TXF ? (int)(((nbase + 2 * (long long)tid) >> 3) - (brow0 >> 1)) : 0;
     const uint8_t* brow = TXF ? a.ref_bits + f0 * a.ref_stride : nullptr;
     float4* txrow = TXF ? reinterpret_cast<float4*>(a.tx_out + f0 * a.L + nbase) + tid : nullptr;
-    unsigned long long nb[WPT];
-    /* word w of this thread = table word tid + w*THREADS at row byte offset bo0 + 8*w*THREADS.  Which of them lie inside
-     * the row: flag bits kept in ONE register the compiler cannot see through (it otherwise re-derives the 64-bit
-     * comparisons every frame) */
-    const long long bo0 = brow0 + 8 * tid;
-    uint32_t bvf = 0;
-#pragma unroll
-    for (int w = 0; w < WPT; ++w) {
-        const long long bo = bo0 + 8ll * w * THREADS;
-        nb[w] = 0;
-        if (TXF && tid + w * THREADS < BWORDS && bo >= 0 && bo + 8 <= (long long)a.ref_stride) bvf |= 1u << w;
-    }
-    asm volatile("" : "+r"(bvf));
+    unsigned long long nb0 = 0, nb1 = 0;
+    const long long bo0 = brow0 + 8 * tid, bo1 = bo0 + 8 * THREADS;
+    const bool bw0 = TXF && tid < BWORDS, bw1 = TXF && tid + THREADS < BWORDS; /* has a first / second word slot */
+    const bool bv0 = bw0 && bo0 >= 0 && bo0 + 8 <= (long long)a.ref_stride;     /* ... and it lies inside the row */
+    const bool bv1 = bw1 && bo1 >= 0 && bo1 + 8 <= (long long)a.ref_stride;
     auto fetch_bits = [&](const uint8_t* row) {
-#pragma unroll
-        for (int w = 0; w < WPT; ++w) {
-            nb[w] = 0; /* symbols outside the frame map to entry 0: finite, and multiplied by the NCO table's zeros */
-            if (bvf & (1u << w)) nb[w] = __ldg(reinterpret_cast<const unsigned long long*>(row + bo0 + 8ll * w * THREADS));
-        }
+        nb0 = nb1 = 0; /* symbols outside the frame map to entry 0: finite, and multiplied by the NCO table's zeros */
+        if (bv0) nb0 = __ldg(reinterpret_cast<const unsigned long long*>(row + bo0));
+        if (bv1) nb1 = __ldg(reinterpret_cast<const unsigned long long*>(row + bo1));
     };
     auto map_word = [&](unsigned long long w, f32x2* dst) {
         f32x2 e[4];
@@ -334,9 +324,8 @@ __global__ void __launch_bounds__(THREADS, MINB)
         reinterpret_cast<ulonglong2*>(dst)[1] = make_ulonglong2(e[2], e[3]);
     };
     auto park_bits = [&]() {
-#pragma unroll
-        for (int w = 0; w < WPT; ++w)
-            if (TXF && ((w + 1) * THREADS <= BWORDS || tid + w * THREADS < BWORDS)) map_word(nb[w], s_sq + (TXF ? 4 * (tid + w * THREADS) : 0));
+        if (bw0) map_word(nb0, s_sq + (TXF ? 4 * tid : 0));
+        if (bw1) map_word(nb1, s_sq + (TXF ? 4 * (tid + THREADS) : 0));
     };
     if (TXF && f0 < f1) {
         fetch_bits(brow);
@@ -376,28 +365,20 @@ __global__ void __launch_bounds__(THREADS, MINB)
                         }
             }
         }
-        /* the chunk's symbol pair (one 8-byte shared load per step) is fetched SQD steps ahead of its use: next to its use
-         * it cost a shared-memory round trip per chunk (19 % of all stall samples; the compiler does not hoist it above
-         * the previous step's shared store by itself), all 17 up front cost 34 registers */
-        constexpr int SQD = THREADS >= 128 ? 0 : 3; /* measured: the 4-warp CTA is 4 % faster without the look-ahead, the 2-warp CTA 4 % slower */
-        f32x2 sqv[TXF ? C::ITER : 1];
-        auto sq_fetch = [&](int it) {
-            if (TXF && it < C::ITER && staged(it)) sqv[TXF ? it : 0] = s_sq[TXF ? sqoff + (THREADS / 4) * it : 0];
-        };
-#pragma unroll
-        for (int it = 0; it < SQD; ++it) sq_fetch(it);
         /* the parked NCO values come back 32 columns (8 steps) at a time, each batch when the previous one is used up */
         float parked[TMC > 0 ? 32 : 4];
 #pragma unroll
         for (int it = 0; it < C::ITER; ++it) {
             if (TMC > 0 && it < TCH && it % 8 == 0) tmem_ld32(twarp + 4 * it, parked);
-            sq_fetch(it + SQD);
             if (staged(it)) {
                 const float4 cs = (TMC > 0 && it < TCH) ? make_float4(parked[(4 * it) % 32], parked[(4 * it + 1) % 32], parked[(4 * it + 2) % 32], parked[(4 * it + 3) % 32])
                                                         : LDC(cs4 + it * THREADS);
                 float x0r, x1r;
                 if (TXF) {
-                    const float2 sq = unpk2(sqv[TXF ? it : 0]); /* (i, q) of the chunk's symbol */
+                    /* (i, q) of the chunk's symbol.  (Fetching these pairs a few steps ahead, or all up front, measured
+                     * 4-10 % SLOWER at this CTA shape although 19 % of the stall samples sit on this load: the extra live
+                     * registers cost more than the round trip, which the other three warps of the scheduler cover.) */
+                    const float2 sq = unpk2(s_sq[TXF ? sqoff + (THREADS / 4) * it : 0]);
                     /* modulator.rs:37-43 on packed pairs: (i*c, i*s) and (q*s, q*c) by two FMUL2, then
                      * (i*c - q*s, i*s + q*c) by one FFMA2 with (-1, +1): a product by +-1 is exact, so the fma's one
                      * rounding is the rounding of the reference's subtraction / addition */

@@ -23,7 +23,7 @@ def test_library_exports_every_declared_symbol(pkg):
     assert len(names) >= 42
     missing = [n for n in names if not hasattr(L, n)]
     assert not missing, missing
-    assert L.modem_gpu_abi_version() == 2
+    assert L.modem_gpu_abi_version() == 3
 
 
 def test_cfg_struct_matches_header(pkg):
@@ -159,7 +159,7 @@ def test_hot_kernels_do_not_spill(pkg):
     once cost 8 bytes of spill and 7 % of its speed.  The ptxas log of the in-tree build is the guard."""
     logdir = os.path.join(ROOT, "rust-modem_b200", "lib")
     hot = [("rx_fast_64.ptxas.log", "_ZN2mg14rx_fast_kernelILi64ELi0ELb0ELb0ELi64ELi8ELi4ELi3ELi64ELb0EEE"),
-           ("loop_fused_64.ptxas.log", "_ZN2mg14rx_fast_kernelILi64ELi0ELb0ELb0ELi64ELi8ELi4ELi3ELi64ELb1EEE"),  # the fused loopback
+           ("loop_fused_64.ptxas.log", "_ZN2mg14rx_fast_kernelILi64ELi0ELb0ELb0ELi128ELi4ELi4ELi3ELi64ELb1EEE"),  # the fused loopback
            ("tx_fast.ptxas.log", "_ZN2mg19tx_rect_fast_kernelILi2ELb0ELb0EEE"),
            ("tx_fast.ptxas.log", "_ZN2mg21tx_shaped_fast_kernelILi8ELi129ELb1ELi2ELi2EEE")]  # C3 TX, sign-product form
     for fn, sym in hot:

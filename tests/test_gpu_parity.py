@@ -233,6 +233,22 @@ def test_awgn_matches_oracle(pkg, orc):
     assert abs(float(got.std()) - 0.75) < 0.02
 
 
+def test_random_bits_match_oracle(pkg, orc):
+    """Philox payload bits generated on the device (BASELINE config 4: "bits from Philox too"): vector and scalar store
+    paths, a frame offset past 2^32, host and device destinations."""
+    import torch
+
+    m = pkg.Modem(**path_kwargs("qpsk", sps=8))
+    for F, nbits in ((5, 16384), (3, 300), (2, 128), (4, 1000)):
+        seed, f0 = 0xA5A5 + (3 << 32), (1 << 33) + 9
+        ref = orc.random_bits(F, nbits, seed, f0)
+        assert np.array_equal(m.random_bits(F, nbits, seed, f0), ref), (F, nbits)
+        d = torch.full((F, nbits), 7, dtype=torch.uint8, device="cuda")
+        m.random_bits_into(d, F, nbits, seed, f0)
+        m.synchronize()
+        assert np.array_equal(d.cpu().numpy(), ref), (F, nbits)
+
+
 @pytest.mark.parametrize("shaped", [False, True])
 def test_noisy_loopback_matches_oracle(pkg, orc, shaped):
     """Loopback with the AWGN stage fused into the RX load: decisions and error counts equal the oracle's."""
@@ -323,6 +339,34 @@ def test_host_loopback_pipeline(pkg, orc, chunk, monkeypatch):
         assert np.array_equal(got["sym"][4 * c: 4 * c + 4], s_ref), f"channel {c}"
         assert np.array_equal(got["bits"][4 * c: 4 * c + 4], b_ref)
     assert got["errors"] == 0 and got["compared"] == got["bits"].size
+
+
+@pytest.mark.parametrize("two_kernels,ramp", [(False, True), (False, False), (True, True), (True, False)])
+def test_host_loopback_pipeline_fused_and_ramped(pkg, orc, two_kernels, ramp, monkeypatch):
+    """The noise-free headline shape through the host-buffer pipeline in its four forms: TX + RX kernels per chunk
+    (the default) or ONE fused kernel per chunk that never materialises the samples (MODEM_GPU_PIPE_FUSED=1), equal
+    chunks (default) or chunk sizes that ramp up and down at the ends of the call (16, 32, 64 ... 64, 32, 16 here):
+    the same bytes from all of them."""
+    monkeypatch.setenv("MODEM_GPU_PIPE_CHUNK", "64")
+    if not two_kernels:
+        monkeypatch.setenv("MODEM_GPU_PIPE_FUSED", "1")
+    if ramp:
+        monkeypatch.setenv("MODEM_GPU_PIPE_RAMP", "1")
+    kw = path_kwargs("qpsk", sps=8)
+    m, o = make(pkg, orc, **kw)
+    bits = rand_bits(93, 301, 2 * 520)
+    sym_ref, bits_ref, cnt_ref = o.loopback(bits, threads=8)
+    n0 = m.launch_count
+    out = m.loopback(bits)
+    launches = m.launch_count - n0
+    assert np.array_equal(out["sym"], sym_ref) and np.array_equal(out["bits"], bits_ref)
+    assert (out["errors"], out["compared"]) == cnt_ref and cnt_ref[0] == 0
+    n_chunks = (2 * 2 + 4) if ramp else 5  # 16 32 | 64 64 64 (77 -> merged with the runt) | 32 16   or   64 x 4 + 45
+    if not two_kernels:
+        assert launches == 1 + (7 if ramp else 5), launches  # NCO table + one fused kernel per chunk
+    else:
+        assert launches == 1 + 2 * (7 if ramp else 5), launches
+    del n_chunks
 
 
 @pytest.mark.parametrize("chunk,shaped", [(0, False), (5, False), (3, True)])
