@@ -337,32 +337,72 @@ __global__ void __launch_bounds__(THREADS, MINB)
         constexpr bool EDGE = decltype(edge_c)::value;
         if (!TXF && PF != 2) load_tile(fr, edge_c);
         if (NOISE) {
-            /* G chunks per trip: their Philox / logf / sqrt / sincos chains are independent, so the scheduler can
-             * interleave them (one chunk per trip left ~2 independent chains per warp at 4 warps per scheduler:
-             * latency-bound); the trip count stays rolled to keep the code in the instruction cache */
+            /* AWGN on the fly (oracle/modem_oracle.h "AWGN"): one Philox block serves an aligned QUAD of samples = the chunks
+             * of two neighbouring lanes, so the lanes of a pair split the generator work -- over two steps the even lane runs
+             * the block of the first step, the odd lane the block of the second, and each hands the other the two words it
+             * does not need itself (two shuffles): one Philox per TWO chunks instead of one per chunk.  Four steps per trip
+             * give every lane two independent Philox chains and four independent Box-Muller evaluations to interleave; the
+             * trip count stays rolled to keep the code in the instruction cache.  When the tile's quads do not start on an
+             * even lane (nbase = 2 mod 4: some even decision delays) every lane runs its own block. */
             constexpr int G = 4;
             const u64 gf = a.nz.frame0 + f;
+            const bool odd = (tid & 1) != 0;
+            const bool paired = ((nbase >> 1) & 1) == 0;
 #pragma unroll 1
             for (int it0 = 0; it0 < C::ITER; it0 += G) {
-                float n0[G], n1[G];
-                bool v[G];
+                uint32_t w0[G], w1[G]; /* the two words of this lane's chunk at step it0 + g */
+                if (paired) {
 #pragma unroll
-                for (int g = 0; g < G; ++g) {
-                    const int it = it0 + g;
-                    const long long n = nbase + 2 * (it * THREADS + tid);
-                    n0[g] = n1[g] = 0.0f;
-                    v[g] = it < C::ITER && it * THREADS + tid < C::NCHUNK && n >= vlo_n && n < vhi_n;
-                    if (v[g]) noise_re_pair(a.nz, gf, (u64)n, &n0[g], &n1[g]); /* n is even: one Philox block per pair */
+                    for (int h = 0; h < G / 2; ++h) {
+                        const int itm = it0 + 2 * h + (odd ? 1 : 0); /* the step whose block this lane runs */
+                        const long long n = nbase + 2 * ((long long)itm * THREADS + (tid & ~1));
+                        uint32_t r[4];
+                        noise_quad(a.nz, gf, (u64)(n >> 2), 0, r);
+                        const uint32_t g0 = __shfl_xor_sync(0xffffffffu, odd ? r[0] : r[2], 1);
+                        const uint32_t g1 = __shfl_xor_sync(0xffffffffu, odd ? r[1] : r[3], 1);
+                        w0[2 * h] = odd ? g0 : r[0];     /* step it0 + 2h: the even lane's block; the odd lane's chunk = words 2, 3 */
+                        w1[2 * h] = odd ? g1 : r[1];
+                        w0[2 * h + 1] = odd ? r[2] : g0; /* step it0 + 2h + 1: the odd lane's block */
+                        w1[2 * h + 1] = odd ? r[3] : g1;
+                    }
+                } else {
+#pragma unroll
+                    for (int g = 0; g < G; ++g) {
+                        const long long n = nbase + 2 * ((long long)(it0 + g) * THREADS + tid);
+                        uint32_t r[4];
+                        noise_quad(a.nz, gf, (u64)(n >> 2), 0, r);
+                        w0[g] = (n & 2) ? r[2] : r[0];
+                        w1[g] = (n & 2) ? r[3] : r[1];
+                    }
                 }
-                /* xr[] must be indexed statically to stay in registers */
+                float n0[G], n1[G];
 #pragma unroll
-                for (int j = 0; j < C::ITER; ++j)
+                for (int g = 0; g < G; ++g) box_muller(w0[g], w1[g], &n0[g], &n1[g]);
+                /* xr[] must be indexed statically to stay in registers: one switch case per trip (a predicated select over
+                 * all ITER x G combinations cost 240 instructions per trip for 16 useful ones) */
+                auto apply = [&](auto trip_c) {
+                    constexpr int T = decltype(trip_c)::value;
 #pragma unroll
-                    for (int g = 0; g < G; ++g)
-                        if (j == it0 + g && v[g]) {
+                    for (int g = 0; g < G; ++g) {
+                        constexpr int JMAX = C::ITER - 1;
+                        const int j = T * G + g < JMAX ? T * G + g : JMAX; /* clamp keeps the index in range for dead iterations */
+                        if (T * G + g < C::ITER && ((vmask >> j) & 1) != 0) {
                             xr[j][0] = __fadd_rn(xr[j][0], __fmul_rn(a.nz.sigma, n0[g]));
                             xr[j][1] = __fadd_rn(xr[j][1], __fmul_rn(a.nz.sigma, n1[g]));
                         }
+                    }
+                };
+                static_assert(C::ITER <= 8 * G, "one switch case per trip");
+                switch (it0 / G) {
+                case 0: apply(std::integral_constant<int, 0>{}); break;
+                case 1: apply(std::integral_constant<int, 1>{}); break;
+                case 2: apply(std::integral_constant<int, 2>{}); break;
+                case 3: apply(std::integral_constant<int, 3>{}); break;
+                case 4: apply(std::integral_constant<int, 4>{}); break;
+                case 5: apply(std::integral_constant<int, 5>{}); break;
+                case 6: apply(std::integral_constant<int, 6>{}); break;
+                default: apply(std::integral_constant<int, 7>{}); break;
+                }
             }
         }
         /* the parked NCO values come back 32 columns (8 steps) at a time, each batch when the previous one is used up */
@@ -612,16 +652,22 @@ cudaError_t rx_fast_launch_t(const RxArgs& a, const float* h_taps, cudaStream_t 
 template <int NT, int THREADS, int MINB, int R, int PF, int TMC>
 cudaError_t rx_fast_dispatch_tmc(const RxArgs& a, const float* h_taps, bool fma, cudaStream_t stream)
 {
-    const bool odd = (a.delay & 1u) != 0; /* OFF = 0 for odd delay, 1 for even */
+    /* OFF shifts the tile so that it starts on an even sample (16-byte pairs): 0 for an odd decision delay, 1 for an even
+     * one.  The noisy kernels want the tile to start on a multiple of FOUR samples (one Philox block = one aligned quad =
+     * the chunks of an even/odd lane pair, rx_fast.cuh phase A), which OFF + 2 provides when OFF alone does not. */
     const bool noise = a.nz.sigma != 0.0f;
+    const uint32_t off = noise ? (4u - (a.delay + 1u) % 4u) % 4u : ((a.delay & 1u) ? 0u : 1u);
 #define MG_RX_CASE(O, F, N) return rx_fast_launch_t<NT, O, F, N, THREADS, MINB, R, PF, TMC>(a, h_taps, stream)
-    if (odd) {
-        if (fma) { if (noise) MG_RX_CASE(0, true, true); else MG_RX_CASE(0, true, false); }
-        else     { if (noise) MG_RX_CASE(0, false, true); else MG_RX_CASE(0, false, false); }
-    } else {
-        if (fma) { if (noise) MG_RX_CASE(1, true, true); else MG_RX_CASE(1, true, false); }
-        else     { if (noise) MG_RX_CASE(1, false, true); else MG_RX_CASE(1, false, false); }
+#define MG_RX_OFF(O)                                                                              \
+    if (fma) { if (noise) MG_RX_CASE(O, true, true); else MG_RX_CASE(O, true, false); }           \
+    else     { if (noise) MG_RX_CASE(O, false, true); else MG_RX_CASE(O, false, false); }
+    switch (off) {
+    case 0: MG_RX_OFF(0)
+    case 1: MG_RX_OFF(1)
+    case 2: if (fma) MG_RX_CASE(2, true, true); else MG_RX_CASE(2, false, true);
+    default: if (fma) MG_RX_CASE(3, true, true); else MG_RX_CASE(3, false, true);
     }
+#undef MG_RX_OFF
 #undef MG_RX_CASE
 }
 template <int NT, int THREADS, int MINB, int R, int PF = RX_DEFAULT_PF, int TMC = RX_DEFAULT_TMC>
