@@ -87,6 +87,9 @@ struct modem_ctx {
     } cs_key;
     bool cs_rx_shared = true; /* every phase offset is 0: the RX view is the TX table */
     u64 chan_version = 0;
+    /* bumped whenever something a captured loopback graph has baked in changes: the NCO tables (rebuilt or re-allocated),
+     * the TX mapper (set_phasor), the stream (set_stream), the bank (set_channels) */
+    u64 graph_epoch = 0;
     cudaEvent_t ev_pool[8] = {};
     size_t loop_chunk = 0; /* MODEM_GPU_LOOP_CHUNK: frames per chunk of the device loopback pipeline */
     /* the chunk pipeline of modem_gpu_loopback_device, captured once per argument set and replayed */
@@ -96,7 +99,7 @@ struct modem_ctx {
         size_t F = 0, nbits = 0, Fc = 0;
         float sigma = 0.0f;
         uint64_t seed = 0, frame0 = 0;
-        u64 chan_version = 0;
+        u64 chan_version = 0, epoch = 0;
     } loop_graph;
     bool use_graph = true; /* MODEM_GPU_NO_GRAPH=1 disables */
     uint64_t launches = 0;
@@ -273,6 +276,10 @@ int attach_carrier_table(modem_ctx* ctx, mg::ChannelView& view, u64 F, u64 len, 
         const u64 row = kCsPadLo + len + kCsPadHi;
         const size_t bytes = key.nch * row * sizeof(float2);
         if (bytes > ((size_t)1 << 30)) return MODEM_OK; /* too many carriers for a table: kernels evaluate the NCO themselves */
+        /* the cached key is void from here on: if anything below fails the tables hold no complete row set, and a captured
+         * graph that baked in their addresses or contents must not be replayed */
+        ctx->cs_key.ver = ~0ull;
+        ctx->graph_epoch++;
         int rc = ensure(ctx, ctx->s_cs_tx, bytes);
         if (rc) return rc;
         mg::ChannelView cv = channel_view(ctx);
@@ -928,6 +935,7 @@ int modem_gpu_set_stream(modem_ctx_t* ctx, void* cuda_stream)
     }
     ctx->stream = static_cast<cudaStream_t>(cuda_stream);
     ctx->own_stream = false;
+    ctx->graph_epoch++;
     return MODEM_OK;
 }
 
@@ -937,6 +945,7 @@ int modem_gpu_set_channels(modem_ctx_t* ctx, size_t n_channels, const float* sam
     if (!ctx) return MODEM_ERR_INVALID;
     CK(ctx, cudaSetDevice(ctx->device));
     CK(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->graph_epoch++;
     if (n_channels == 0) {
         ctx->n_channels = 0;
         ctx->frames_per_channel = 1;
@@ -1001,6 +1010,7 @@ int modem_gpu_modulate(modem_ctx_t* ctx, const uint8_t* bits, size_t F, size_t n
 int modem_gpu_set_phasor(modem_ctx_t* ctx, const modem_phasor_t* ph)
 {
     if (!ctx) return MODEM_ERR_INVALID;
+    ctx->graph_epoch++;
     if (!ph || ph->kind == MODEM_PHASOR_TABLE) {
         ctx->phasor_on = false;
         return MODEM_OK;
@@ -1513,7 +1523,7 @@ int modem_gpu_loopback_device(modem_ctx_t* ctx, const uint8_t* bits, size_t F, s
     auto& g = ctx->loop_graph;
     const bool same = g.exec && g.bits == bits && g.tx == d_tx && g.sym == sym && g.out == bits_out && g.cnt == counters &&
                       g.F == F && g.nbits == nbits && g.Fc == Fc && g.sigma == sigma && g.seed == seed && g.frame0 == frame0 &&
-                      g.chan_version == ctx->chan_version;
+                      g.chan_version == ctx->chan_version && g.epoch == ctx->graph_epoch;
     if (ctx->use_graph && cap == cudaStreamCaptureStatusNone && F > Fc) {
         if (!same) {
             if (g.exec) {
@@ -1547,6 +1557,7 @@ int modem_gpu_loopback_device(modem_ctx_t* ctx, const uint8_t* bits, size_t F, s
             g.bits = bits; g.tx = d_tx; g.sym = sym; g.out = bits_out; g.cnt = counters;
             g.F = F; g.nbits = nbits; g.Fc = Fc; g.sigma = sigma; g.seed = seed; g.frame0 = frame0;
             g.chan_version = ctx->chan_version;
+            g.epoch = ctx->graph_epoch;
             return MODEM_OK;
         }
         CK(ctx, cudaGraphLaunch(g.exec, user));

@@ -418,6 +418,43 @@ def test_device_loopback_pipeline(pkg, orc, chunk, shaped, monkeypatch):
         assert np.array_equal(d_s2[5 * c: 5 * c + 5].cpu().numpy(), s_ref), f"channel {c}"
 
 
+def test_loop_graph_cache_survives_table_rebuilds(pkg, orc, monkeypatch):
+    """The chunked device loopback replays a captured CUDA graph when the same call repeats.  The graph bakes in the NCO
+    table's address and contents: a call with longer frames in between re-allocates and rebuilds that table, after which
+    the old graph must not be replayed (it would read freed memory or the wrong carrier values)."""
+    import torch
+
+    monkeypatch.setenv("MODEM_GPU_LOOP_CHUNK", "5")
+    kw = path_kwargs("qpsk", sps=8, shaped=True)  # two-kernel path: the chunk pipeline and its graph
+    m, o = make(pkg, orc, **kw)
+    m.set_stream(torch.cuda.current_stream().cuda_stream)
+
+    def run(bits, d):
+        F, nbits = bits.shape
+        d["cnt"].zero_()
+        m.loopback_device_into(d["bits"], F, nbits, d["cnt"], tx=d["tx"], sym=d["sym"], bits_out=d["out"])
+        torch.cuda.synchronize()
+        return d["tx"].cpu().numpy(), d["sym"].cpu().numpy(), tuple(d["cnt"].tolist())
+
+    def bufs(bits):
+        F, nbits = bits.shape
+        L = m.frame_samples(nbits); K = m.decided_symbols(L)
+        return dict(bits=torch.from_numpy(bits).cuda(), tx=torch.empty((F, L, 2), dtype=torch.float32, device="cuda"),
+                    sym=torch.empty((F, K), dtype=torch.uint8, device="cuda"), out=torch.empty((F, 2 * K), dtype=torch.uint8, device="cuda"),
+                    cnt=torch.zeros(2, dtype=torch.int64, device="cuda"))
+
+    a, b = rand_bits(97, 22, 2 * 600), rand_bits(98, 22, 2 * 2000)
+    da, db = bufs(a), bufs(b)
+    ref = {}
+    for name, bits in (("a", a), ("b", b)):
+        sym_ref, _, cnt_ref = o.loopback(bits, threads=4)
+        ref[name] = (o.modulate(bits), sym_ref, cnt_ref)
+    for name, bits, d in (("a", a, da), ("a", a, da), ("b", b, db), ("a", a, da), ("b", b, db), ("a", a, da)):
+        tx, sym, cnt = run(bits, d)
+        assert_buffers(tx, ref[name][0], f"tx of call {name}")
+        assert np.array_equal(sym, ref[name][1]) and cnt == ref[name][2], name
+
+
 def test_ber_sweep_matches_oracle(pkg, orc):
     """BASELINE config 4 in miniature: Eb/N0 sweep, modulate once, per-point counters equal the oracle's
     (noise key = seed + point, counter = global frame id), and two 'ranks' with disjoint frame ranges add up."""
