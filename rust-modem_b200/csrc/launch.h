@@ -16,13 +16,18 @@ struct LaunchGeom {
 };
 
 /* rx_fast_<NT>.cu: sps 8, NT taps */
-bool rx_fast_supported(uint32_t n_taps);
+bool rx_fast_supported(uint32_t n_taps, bool fma, bool tmem);
 uint64_t rx_fast_tiles(uint32_t n_taps, uint64_t K);
 cudaError_t rx_fast_launch(const RxArgs& a, const float* h_taps, bool fma, bool tmem, cudaStream_t stream);
 /* fused loopback (loop_fused_64.cu): TX samples made and stored by the demodulating kernel itself */
 uint64_t loop_fused_tile_symbols_64();
 bool loop_fused_supported_64(const RxArgs& a);
 cudaError_t loop_fused_launch_64(const RxArgs& a, const float* h_taps, bool tmem, cudaStream_t stream);
+
+/* rx_dec.cu: tuned decimating RX for any samples-per-symbol count (the reference's default rates: 45), 64 taps */
+bool rx_dec_supported(uint32_t n_taps, uint32_t sps);
+uint32_t rx_dec_tile_symbols(uint32_t sps);
+cudaError_t rx_dec_launch(const RxArgs& a, const float* h_taps, bool fma, bool tmem, cudaStream_t stream);
 
 /* rx_fullrate_fast.cu: the full-rate (I,Q) stream, 64 taps; needs L even and a 16-byte aligned filt row base */
 bool rx_fullrate_fast_supported(uint32_t n_taps);

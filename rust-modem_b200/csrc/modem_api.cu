@@ -107,6 +107,7 @@ struct modem_ctx {
     bool pipe_trace = false; /* MODEM_GPU_PIPE_TRACE=1: per-chunk event timeline of the host-buffer pipeline on stderr */
     bool pipe_fused = false; /* MODEM_GPU_PIPE_FUSED=1: the host-buffer pipeline runs the fused loopback kernel per chunk instead of TX + RX (measured slower, see loopback_pipelined) */
     bool pipe_ramp = false; /* MODEM_GPU_PIPE_RAMP=1: short chunks at both ends of the call (measured slower with TX + RX, a wash with the fused kernel) */
+    bool no_rx_dec = false; /* MODEM_GPU_NO_RX_DEC=1: shapes of the tuned any-sps RX kernel (rx_dec.cu) take the generic kernel */
     bool no_sign_slice = false; /* MODEM_GPU_NO_SIGN_SLICE=1: the fast RX kernel always runs the nearest-point search */
     bool no_fused_loop = false; /* MODEM_GPU_NO_FUSED_LOOP=1: the loopback entries run the TX and the RX kernel separately */
     int rx_fpb = 0, rx_tile_major = -1; /* MODEM_GPU_RX_FPB / MODEM_GPU_RX_TILEMAJOR: tuning knobs */
@@ -500,7 +501,7 @@ int launch_rx(modem_ctx* ctx, const float2* d_rx, u64 F, u64 L, uint8_t* d_sym, 
     if (a.K == 0 || !(d_sym || d_bits || d_soft || d_ref)) return MODEM_OK;
 
     const bool fast_ok = !src && !ctx->force_generic && sps == 8 && c.q_offset == 0 && (L % 2 == 0) && aligned16(d_rx) &&
-                         mg::rx_fast_supported(N);
+                         mg::rx_fast_supported(N, fma, !(c.flags & MODEM_FLAG_NO_TMEM));
     if (fast_ok) {
         a.frames_per_block = frames_per_block(ctx, F, mg::rx_fast_tiles(N, a.K));
         if (ctx->rx_fpb > 0 && !ctx->n_channels) a.frames_per_block = (uint32_t)std::max<u64>(ctx->rx_fpb, (F + 65534) / 65535);
@@ -512,6 +513,16 @@ int launch_rx(modem_ctx* ctx, const float2* d_rx, u64 F, u64 L, uint8_t* d_sym, 
         if (!a.ch.cs_tab) return fail(ctx, MODEM_ERR_UNSUPPORTED, "carrier bank too large for the NCO table (> 1 GiB)");
         set_sign_slicer(ctx, a);
         CK(ctx, mg::rx_fast_launch(a, ctx->h_rx_taps.data(), fma, !(c.flags & MODEM_FLAG_NO_TMEM), ctx->stream));
+    } else if (!src && !ctx->force_generic && !ctx->no_rx_dec && c.q_offset == 0 && sigma == 0.0f && (L % 2 == 0) && aligned16(d_rx) &&
+               mg::rx_dec_supported(N, sps)) {
+        /* any other samples-per-symbol count with the 64-tap low-pass (the reference's default rates: sps 45) */
+        a.sym_tile = mg::rx_dec_tile_symbols(sps);
+        a.frames_per_block = frames_per_block(ctx, F, (a.K + a.sym_tile - 1) / a.sym_tile);
+        int rc = attach_carrier_table(ctx, a.ch, F, L, true);
+        if (rc) return rc;
+        if (!a.ch.cs_tab) return fail(ctx, MODEM_ERR_UNSUPPORTED, "carrier bank too large for the NCO table (> 1 GiB)");
+        set_sign_slicer(ctx, a);
+        CK(ctx, mg::rx_dec_launch(a, ctx->h_rx_taps.data(), fma, !(c.flags & MODEM_FLAG_NO_TMEM), ctx->stream));
     } else {
         size_t budget = 96 * 1024;
         if ((size_t)N * 4 + (size_t)(N + c.q_offset) * 17 + 64 > budget)
@@ -858,6 +869,8 @@ int modem_gpu_create(modem_ctx_t** out, int device, const modem_cfg_t* cfg)
     ctx->pipe_trace = ptr && ptr[0] == '1';
     const char* nf = getenv("MODEM_GPU_NO_FUSED_LOOP");
     ctx->no_fused_loop = nf && nf[0] == '1';
+    const char* nrd = getenv("MODEM_GPU_NO_RX_DEC");
+    ctx->no_rx_dec = nrd && nrd[0] == '1';
     const char* nss = getenv("MODEM_GPU_NO_SIGN_SLICE");
     ctx->no_sign_slice = nss && nss[0] == '1';
     const char* rf = getenv("MODEM_GPU_RX_FPB");

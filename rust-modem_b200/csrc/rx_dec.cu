@@ -1,0 +1,200 @@
+/*
+ * rx_dec.cu -- tuned decimating RX for ANY samples-per-symbol count (the reference's default rates give 45:
+ * rates.rs:16 with src/bin/modulate.rs:44-58) and the reference's 64-tap low-pass (src/bin/demodulate.rs:82-147).
+ * Replaces demodulator.rs:44-55 + two fir.rs:18-34 filters of the reference plus the decimator / slicer / error-count
+ * extension, like rx_fast.cuh does for 8 samples per symbol; the generic kernel (kernels.cuh) keeps the shapes this one
+ * does not take (per-frame PLL offsets, raw wire formats, an OQPSK rail offset, noise, odd frame lengths).
+ *
+ * At sps = 45 the FIR is 2.8 MACs per sample (64 taps x 2 rails per 45 samples): the kernel is a stream of 8 B/sample
+ * from HBM and must be organised like one.
+ *   phase A  the tile's samples are read two at a time (128-bit loads, eight per thread in flight before the first use; the
+ *            next frame's tile is pulled towards L2 by one bulk prefetch per CTA meanwhile),
+ *            their real parts multiplied by the NCO pair (cos, sin) from the context's table (ChannelView::cs_tab, read
+ *            through L1/L2: frame-invariant) and staged as packed (x cos, x sin) pairs, one 128-bit shared store per
+ *            sample pair.  The Q rail is staged NEGATED (x sin instead of x (-sin)): see rx_fast.cuh -- exact, and
+ *            phase C takes 0 - acc.
+ *   phase B  one thread = one symbol, both rails packed: 64 ordered MACs (FMUL2 + FFMA2 with (1, 1), products one step
+ *            ahead of their accumulation), each fed by one 8-byte shared load; the taps are uniform operands from the
+ *            constant bank.  Threads read the staged row at a stride of sps pairs: conflict-free for odd sps.
+ *   phase C  slice (sign test for an axis-aligned 4-point table, else nearest point), emit, count.
+ */
+#include <atomic>
+
+#include "launch.h"
+#include "rx_fast.cuh" /* the tensor-memory helpers */
+
+namespace mg {
+
+constexpr int kDecThreads = 128; /* = symbols per tile */
+
+/* TMEM: the frame-invariant NCO values of a thread's first 32 chunks (128 values) are parked in tensor memory once per CTA
+ * (128 columns x 4 CTAs = the SM's 512 columns, all 128 lanes used) and read back with tcgen05.ld every frame, instead of
+ * 8 B/sample from the NCO table through L2/L1 next to the 8 B/sample of the signal itself. */
+template <int NT, bool FMA, bool TMEM>
+__global__ void __launch_bounds__(kDecThreads, 4)
+    rx_dec_kernel(const __grid_constant__ RxArgs a, const __grid_constant__ TapsParam<NT> taps)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    f32x2* s_v = reinterpret_cast<f32x2*>(smem_raw); /* staged (x cos, x sin) pairs, index = sample - nb0 */
+    __shared__ float2 s_slut[kMaxLut];
+    const int tid = threadIdx.x & (kDecThreads - 1);
+    for (uint32_t i = tid; i < a.n_tables * a.n_const; i += kDecThreads) s_slut[i] = a.slut[i];
+
+    const uint32_t TS = a.sym_tile, sps = a.sps;
+    const u64 f0 = (u64)blockIdx.y * a.frames_per_block;
+    const u64 f1 = min(a.F, f0 + a.frames_per_block);
+    const u64 k0 = (u64)blockIdx.x * TS;
+    /* first sample the tile's first symbol needs (may be negative: zero history, fir.rs:13), floored to an even index so
+     * that sample pairs are the 16-byte pairs of the row */
+    const long long nb = (long long)(k0 * sps + a.delay) - (long long)(NT - 1);
+    const long long nb0 = nb & ~1ll;
+    const uint32_t shift = (uint32_t)(nb - nb0);
+    const uint32_t R = (TS - 1) * sps + NT + shift; /* samples staged */
+    const uint32_t NCH = (R + 1) / 2;               /* 16-byte chunks */
+    const float4* cs4 = reinterpret_cast<const float4*>(chan_table(a.ch, f0) + nb0);
+    const f32x2 one = pk2(taps.one.x, taps.one.y);
+    const u64 k = k0 + tid;
+    const bool live = (uint32_t)tid < TS && k < a.K;
+    const f32x2* mine = s_v + (size_t)tid * sps + (NT - 1) + shift; /* the decision instant of this thread's symbol */
+    const bool lut4 = a.n_const == 4 && a.n_tables == 1;
+    const uint32_t toff = (uint32_t)(k % a.n_tables) * a.n_const;
+
+    constexpr int U = 8;        /* chunks per thread and trip: all loads of a trip are in flight before the first use */
+    constexpr int TRIPS_TM = 4; /* trips whose NCO values live in tensor memory: 4 x 8 chunks x 4 values = 128 columns */
+    __shared__ uint32_t s_tmem;
+    uint32_t taddr = 0, twarp = 0;
+    auto chunk_ok = [&](uint32_t c) {
+        const long long n = nb0 + 2 * (long long)c;
+        return c < NCH && n >= 0 && (u64)n < a.L; /* L is even: a pair is inside or outside */
+    };
+    if (TMEM) {
+        taddr = tmem_alloc<128>(&s_tmem);
+        twarp = tmem_warp_addr(taddr);
+#pragma unroll
+        for (int b = 0; b < TRIPS_TM; ++b) {
+            float park[32];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const uint32_t c = tid + (b * U + u) * kDecThreads;
+                const float4 t = chunk_ok(c) ? __ldg(cs4 + c) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                park[4 * u] = t.x; park[4 * u + 1] = t.y; park[4 * u + 2] = t.z; park[4 * u + 3] = t.w;
+            }
+            tmem_st32(twarp + 32 * b, park);
+        }
+    }
+
+    uint32_t err = 0, cmp = 0;
+    for (u64 f = f0; f < f1; ++f) {
+        __syncthreads(); /* previous frame's FIR finished; s_slut visible */
+        const float4* src = reinterpret_cast<const float4*>(a.rx + f * a.L + nb0);
+        /* pull the NEXT frame's tile towards L2 while this one is staged and filtered: one bulk (TMA) prefetch per CTA */
+        if (tid == 0 && f + 1 < f1) {
+            const long long lo = nb0 < 0 ? 0 : nb0, hi = min((long long)a.L, nb0 + 2 * (long long)NCH);
+            if (hi > lo) {
+                const char* nxt = reinterpret_cast<const char*>(a.rx + (f + 1) * a.L + lo);
+                asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(nxt), "r"((int)(hi - lo) * 8) : "memory");
+            }
+        }
+        auto stage = [&](uint32_t c, const float4& x, const float4& cs) { /* demodulator.rs:53-54, Q rail negated (see the header) */
+            reinterpret_cast<ulonglong2*>(s_v)[c] = make_ulonglong2(mul2(pk2(x.x, x.x), pk2(cs.x, cs.y)), mul2(pk2(x.z, x.z), pk2(cs.z, cs.w)));
+        };
+        uint32_t c0 = tid;
+        if (TMEM) {
+#pragma unroll
+            for (int b = 0; b < TRIPS_TM; ++b, c0 += U * kDecThreads) {
+                if (c0 - tid >= NCH) break; /* uniform: the tile has no more chunks */
+                float4 x[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const uint32_t c = c0 + u * kDecThreads;
+                    x[u] = chunk_ok(c) ? __ldg(src + c) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                }
+                float parked[32];
+                tmem_ld32(twarp + 32 * b, parked);
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const uint32_t c = c0 + u * kDecThreads;
+                    if (c < NCH) stage(c, x[u], make_float4(parked[4 * u], parked[4 * u + 1], parked[4 * u + 2], parked[4 * u + 3]));
+                }
+            }
+        }
+        for (; c0 < NCH; c0 += U * kDecThreads) { /* chunks beyond the parked ones (large sps), or all of them without TMEM */
+            float4 x[U], cs[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const uint32_t c = c0 + u * kDecThreads;
+                const bool ok = chunk_ok(c);
+                x[u] = ok ? __ldg(src + c) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                cs[u] = ok ? __ldg(cs4 + c) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const uint32_t c = c0 + u * kDecThreads;
+                if (c < NCH) stage(c, x[u], cs[u]);
+            }
+        }
+        __syncthreads();
+        if (live) {
+            /* fir.rs:21-24 on both rails at once: acc = fl(acc + fl(v * h)), taps 0..NT-1 in order */
+            f32x2 acc = 0ull, pend = 0ull;
+#pragma unroll
+            for (int i = 0; i < NT; ++i) {
+                const f32x2 v = mine[-i];
+                const f32x2 hh = pk2(taps.hh[i].x, taps.hh[i].y);
+                if (FMA) {
+                    acc = fma2(v, hh, acc);
+                } else {
+                    const f32x2 prod = mul2(v, hh);
+                    if (i > 0) acc = fma2(acc, one, pend);
+                    pend = prod;
+                }
+            }
+            if (!FMA) acc = fma2(acc, one, pend);
+            const float2 t = unpk2(acc);
+            const float I = __fmul_rn(a.rx_gain, t.x), Q = __fmul_rn(a.rx_gain, __fsub_rn(0.0f, t.y));
+            uint32_t s;
+            if (a.sign_slice && fabsf(I) >= a.ss_lo && fabsf(I) <= a.ss_hi && fabsf(Q) >= a.ss_lo && fabsf(Q) <= a.ss_hi)
+                s = ((~__float_as_uint(I) >> 31) << 1) | (~__float_as_uint(Q) >> 31);
+            else
+                s = lut4 ? slice_point(s_slut, 4, I, Q) : slice_point(s_slut + toff, a.n_const, I, Q);
+            err += emit_symbol(a, f, k, s, I, Q);
+            cmp += a.ref_bits ? a.bps : 0u;
+        }
+    }
+    block_count(a, err, cmp);
+    if (TMEM) tmem_free<128>(taddr);
+}
+
+bool rx_dec_supported(uint32_t n_taps, uint32_t sps) { return n_taps == 64 && sps >= 2 && sps <= 180; }
+uint32_t rx_dec_tile_symbols(uint32_t sps)
+{
+    (void)sps;
+    return kDecThreads; /* (127 sps + 66) * 8 B of shared memory: 46 KB at sps 45, 183 KB at sps 180 */
+}
+template <int NT, bool FMA, bool TMEM>
+static cudaError_t rx_dec_launch_t(const RxArgs& a, const float* h_taps, cudaStream_t stream)
+{
+    const size_t smem = ((size_t)(a.sym_tile - 1) * a.sps + NT + 2) * sizeof(f32x2);
+    auto kern = rx_dec_kernel<NT, FMA, TMEM>;
+    static std::atomic<size_t> configured[kMaxDevices]; /* per device: the attribute is per device */
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev < 0 || dev >= kMaxDevices || configured[dev].load(std::memory_order_acquire) != smem + 1) {
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        if (e != cudaSuccess) return e;
+        if (dev >= 0 && dev < kMaxDevices) configured[dev].store(smem + 1, std::memory_order_release);
+    }
+    dim3 grid((unsigned)((a.K + a.sym_tile - 1) / a.sym_tile), (unsigned)((a.F + a.frames_per_block - 1) / a.frames_per_block));
+    kern<<<grid, kDecThreads, smem, stream>>>(a, make_taps_param<NT>(h_taps));
+    return cudaGetLastError();
+}
+cudaError_t rx_dec_launch(const RxArgs& a, const float* h_taps, bool fma, bool tmem, cudaStream_t stream)
+{
+    if (tmem) return fma ? rx_dec_launch_t<64, true, true>(a, h_taps, stream) : rx_dec_launch_t<64, false, true>(a, h_taps, stream);
+    return fma ? rx_dec_launch_t<64, true, false>(a, h_taps, stream) : rx_dec_launch_t<64, false, false>(a, h_taps, stream);
+}
+
+} /* namespace mg */

@@ -647,34 +647,39 @@ cudaError_t rx_fast_launch_t(const RxArgs& a, const float* h_taps, cudaStream_t 
     return cudaGetLastError();
 }
 
-/* all (OFF, FMA, NOISE) combinations of one (NT, THREADS, MINB); tmem = false (MODEM_FLAG_NO_TMEM) selects the
- * instantiation that keeps every NCO value in L1 and allocates no tensor memory */
+/* The instantiations of one (NT, THREADS, MINB, R, PF, TMC) shape, split into the noise-free and the noisy family so that
+ * each lives in its own translation unit (the 129-tap noisy kernels take minutes to compile).
+ * OFF shifts the tile so that it starts on an even sample (16-byte pairs): 0 for an odd decision delay, 1 for an even
+ * one.  The noisy kernels prefer a tile that starts on a multiple of FOUR samples (one Philox block = one aligned quad =
+ * the chunks of an even/odd lane pair, phase A); OFF = 3 provides that for decision delays that are multiples of 4 (the
+ * matched-filter pair: delay 128), OFF = 0 already does for delay = 3 mod 4 (35); the other two residues run the
+ * OFF = 0 / 1 kernels with every lane generating its own block.  tmem = false (MODEM_FLAG_NO_TMEM) selects instantiations
+ * that allocate no tensor memory; they exist for the exact MAC only (rx_fast_supported). */
 template <int NT, int THREADS, int MINB, int R, int PF, int TMC>
-cudaError_t rx_fast_dispatch_tmc(const RxArgs& a, const float* h_taps, bool fma, cudaStream_t stream)
+cudaError_t rx_fast_dispatch_clean(const RxArgs& a, const float* h_taps, bool fma, bool tmem, cudaStream_t stream)
 {
-    /* OFF shifts the tile so that it starts on an even sample (16-byte pairs): 0 for an odd decision delay, 1 for an even
-     * one.  The noisy kernels want the tile to start on a multiple of FOUR samples (one Philox block = one aligned quad =
-     * the chunks of an even/odd lane pair, rx_fast.cuh phase A), which OFF + 2 provides when OFF alone does not. */
-    const bool noise = a.nz.sigma != 0.0f;
-    const uint32_t off = noise ? (4u - (a.delay + 1u) % 4u) % 4u : ((a.delay & 1u) ? 0u : 1u);
-#define MG_RX_CASE(O, F, N) return rx_fast_launch_t<NT, O, F, N, THREADS, MINB, R, PF, TMC>(a, h_taps, stream)
-#define MG_RX_OFF(O)                                                                              \
-    if (fma) { if (noise) MG_RX_CASE(O, true, true); else MG_RX_CASE(O, true, false); }           \
-    else     { if (noise) MG_RX_CASE(O, false, true); else MG_RX_CASE(O, false, false); }
+    const bool odd = (a.delay & 1u) != 0;
+#define MG_RX_CASE(O, F, T) return rx_fast_launch_t<NT, O, F, false, THREADS, MINB, R, PF, T>(a, h_taps, stream)
+    if (!tmem) { if (odd) MG_RX_CASE(0, false, 0); else MG_RX_CASE(1, false, 0); }
+    if (odd) { if (fma) MG_RX_CASE(0, true, TMC); else MG_RX_CASE(0, false, TMC); }
+    if (fma) MG_RX_CASE(1, true, TMC); else MG_RX_CASE(1, false, TMC);
+#undef MG_RX_CASE
+}
+template <int NT, int THREADS, int MINB, int R, int PF, int TMC>
+cudaError_t rx_fast_dispatch_noise(const RxArgs& a, const float* h_taps, bool fma, bool tmem, cudaStream_t stream)
+{
+    const uint32_t off = (a.delay % 4u == 0) ? 3u : ((a.delay & 1u) ? 0u : 1u);
+#define MG_RX_CASE(O, F, T) return rx_fast_launch_t<NT, O, F, true, THREADS, MINB, R, PF, T>(a, h_taps, stream)
+#define MG_RX_OFF(O)                                                    \
+    if (!tmem) MG_RX_CASE(O, false, 0);                                 \
+    if (fma) MG_RX_CASE(O, true, TMC); else MG_RX_CASE(O, false, TMC);
     switch (off) {
     case 0: MG_RX_OFF(0)
     case 1: MG_RX_OFF(1)
-    case 2: if (fma) MG_RX_CASE(2, true, true); else MG_RX_CASE(2, false, true);
-    default: if (fma) MG_RX_CASE(3, true, true); else MG_RX_CASE(3, false, true);
+    default: MG_RX_OFF(3)
     }
 #undef MG_RX_OFF
 #undef MG_RX_CASE
-}
-template <int NT, int THREADS, int MINB, int R, int PF = RX_DEFAULT_PF, int TMC = RX_DEFAULT_TMC>
-cudaError_t rx_fast_dispatch(const RxArgs& a, const float* h_taps, bool fma, bool tmem, cudaStream_t stream)
-{
-    if (!tmem) return rx_fast_dispatch_tmc<NT, THREADS, MINB, R, PF, 0>(a, h_taps, fma, stream);
-    return rx_fast_dispatch_tmc<NT, THREADS, MINB, R, PF, TMC>(a, h_taps, fma, stream);
 }
 
 } /* namespace mg */

@@ -1,5 +1,5 @@
-/* rx_fast_129.cu -- instantiations of the fast RX kernel for the 129-tap root-raised-cosine
- * matched filter (span 16 symbols x 8 samples/symbol + 1). */
+/* rx_fast_129.cu -- noise-free instantiations of the fast RX kernel for the 129-tap root-raised-cosine
+ * matched filter (span 16 symbols x 8 samples/symbol + 1); the noisy ones are in rx_fast_129n.cu. */
 #include "launch.h"
 #include "rx_fast.cuh"
 
@@ -13,12 +13,11 @@
 #endif
 
 namespace mg {
+cudaError_t rx_fast_launch_129n(const RxArgs&, const float*, bool, bool, cudaStream_t);
 cudaError_t rx_fast_launch_129(const RxArgs& a, const float* h_taps, bool fma, bool tmem, cudaStream_t stream)
 {
-    /* the noisy variants carry the Philox / Box-Muller state on top of the FIR's registers: give them the roomier
-     * 8-CTA shape (the 10-CTA shape spills there) */
-    if (a.nz.sigma != 0.0f) return rx_fast_dispatch<129, 64, 8, 4, RX_DEFAULT_PF, 64>(a, h_taps, fma, tmem, stream);
-    return rx_fast_dispatch<129, RX129_THREADS, RX129_MINB, RX129_R, RX_DEFAULT_PF, RX129_TMC>(a, h_taps, fma, tmem, stream);
+    if (a.nz.sigma != 0.0f) return rx_fast_launch_129n(a, h_taps, fma, tmem, stream);
+    return rx_fast_dispatch_clean<129, RX129_THREADS, RX129_MINB, RX129_R, RX_DEFAULT_PF, RX129_TMC>(a, h_taps, fma, tmem, stream);
 }
 uint64_t rx_fast_tiles_129(uint64_t K)
 {

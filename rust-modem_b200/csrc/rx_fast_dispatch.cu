@@ -7,7 +7,8 @@ cudaError_t rx_fast_launch_129(const RxArgs&, const float*, bool, bool, cudaStre
 uint64_t rx_fast_tiles_64(uint64_t);
 uint64_t rx_fast_tiles_129(uint64_t);
 
-bool rx_fast_supported(uint32_t n_taps) { return n_taps == 64 || n_taps == 129; }
+/* the no-TMEM instantiations exist for the exact MAC only */
+bool rx_fast_supported(uint32_t n_taps, bool fma, bool tmem) { return (n_taps == 64 || n_taps == 129) && (tmem || !fma); }
 uint64_t rx_fast_tiles(uint32_t n_taps, uint64_t K) { return n_taps == 64 ? rx_fast_tiles_64(K) : rx_fast_tiles_129(K); }
 cudaError_t rx_fast_launch(const RxArgs& a, const float* h_taps, bool fma, bool tmem, cudaStream_t stream)
 {
