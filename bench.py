@@ -306,8 +306,7 @@ def other_configs(pkg, torch, dist, world, rank, local_rank, peak, which, steps=
         dbs = list(range(11))
         sig = [m.sigma_for_ebn0(float(d)) for d in dbs]
         K = m.decided_symbols(L)
-        gen = torch.Generator(device="cuda").manual_seed(0xA5A5 + rank)
-        bits = torch.randint(0, 2, (F, nbits), dtype=torch.uint8, device="cuda", generator=gen)
+        bits = torch.empty((F, nbits), dtype=torch.uint8, device="cuda")
         tx = torch.empty((F, L, 2), dtype=torch.float32, device="cuda")
         cnt = torch.zeros((11, 2), dtype=torch.int64, device="cuda")
         ev = events(3)
@@ -315,6 +314,7 @@ def other_configs(pkg, torch, dist, world, rank, local_rank, peak, which, steps=
             cnt.zero_()
             e = ev[i - 1] if i >= 1 else None
             if e: e[0].record(stream)
+            m.random_bits_into(bits, F, nbits, 0xA5A5 + i, frame0=rank * F)  # payload bits from Philox, in the library
             m.ber_sweep_into(bits, F, nbits, sig, cnt, seed=0xA5A5 + i, frame0=rank * F, tx=tx)
             if e: e[1].record(stream)
         torch.cuda.synchronize()
@@ -327,7 +327,7 @@ def other_configs(pkg, torch, dist, world, rank, local_rank, peak, which, steps=
         m.close()
         del tx
         torch.cuda.empty_cache()
-        return {"config": "C4-style AWGN sweep", "note": "QPSK, sps 8, 129-tap RRC both sides, Eb/N0 0..10 dB: modulate once, 11 noisy demodulations (Philox4x32-10 AWGN added while loading), steady state (warm sweep first, bits and NCCL set-up outside the timer)",
+        return {"config": "C4-style AWGN sweep", "note": "QPSK, sps 8, 129-tap RRC both sides, Eb/N0 0..10 dB: per sweep: Philox payload bits (library), modulate once, 11 noisy demodulations (Philox4x32-10 AWGN added while loading); steady state (warm sweep first, NCCL set-up outside the timer)",
                 "frames_per_gpu": F, "samples_per_frame": L, "ms": round(ms, 3), "points": 11,
                 "Msamples_s": round(world * 11 * n / ms / 1e3, 0), "Gbit_s": round(world * 11 * F * K * BPS / ms / 1e6, 2),
                 "ber_0dB": float(c[0, 0]) / float(c[0, 1]), "ber_0dB_theory": 0.5 * math.erfc(1.0),

@@ -1,5 +1,19 @@
 /*
- * libm_f32.h -- float sin/cos/log evaluated in IEEE binary64, for host AND device.
+ * libm_f32.h -- binary32 sin/cos (evaluated in IEEE binary64) and atan/atan2 for host AND device, bit-identical to
+ * glibc 2.39.
+ *
+ * Third-party algorithms restated here (not code of the reference, which has none of this):
+ *   - sincosf: the algorithm and constants of ARM "optimized-routines" math/sincosf.c, sincosf.h, sincosf_data.c, which
+ *     glibc ships as sysdeps/ieee754/flt-32/s_sincosf.c.  Copyright (c) 2018-2019 Arm Limited; SPDX-License-Identifier:
+ *     MIT (optimized-routines) / LGPL-2.1-or-later as distributed in glibc.  The MIT notice: "Permission is hereby
+ *     granted, free of charge, to any person obtaining a copy of this software and associated documentation files ...
+ *     THE SOFTWARE IS PROVIDED "AS IS", WITHOUT WARRANTY OF ANY KIND".
+ *   - atanf / atan2f: the fdlibm routines s_atanf.c / e_atan2f.c (conversion to float by Ian Lance Taylor, Cygnus
+ *     Support).  "Copyright (C) 1993 by Sun Microsystems, Inc. All rights reserved.  Developed at SunPro, a Sun
+ *     Microsystems, Inc. business.  Permission to use, copy, modify, and distribute this software is freely granted,
+ *     provided that this notice is preserved."
+ * (Round 1 also carried glibc's logf for the Box-Muller stage; the AWGN extension is now defined as explicit binary32
+ * operations -- oracle/modem_oracle.h -- and needs no library logarithm.)
  *
  * Why this exists: the reference computes its NCO with Rust `f32::sin_cos`
  * (/root/reference/src/modem/modulator.rs:46) and `f32::cos` / `f32::sin`
@@ -7,11 +21,11 @@
  * libm `sinf` / `cosf`.  CUDA's `sinf/cosf` are 1-2 ULP routines and are NOT
  * bit-identical to that.  B200 has a full-rate FP64 pipe (half the FP32 rate), so
  * we evaluate the same published algorithm the platform libm uses -- the
- * "optimized-routines" single-precision sincosf / logf (range reduction by pi/2 in
+ * "optimized-routines" single-precision sincosf (range reduction by pi/2 in
  * binary64, two short binary64 polynomials, one final rounding to binary32) -- with
  * the same constants and the same operation order.  Every operation is a correctly
  * rounded IEEE binary64 op on both sides, so the result is bit-identical to glibc
- * 2.39 `sinf/cosf/logf` (verified exhaustively on the host by tools/check_libm.c;
+ * 2.39 `sinf/cosf` (verified exhaustively on the host by tools/check_libm.c;
  * the same header is what the kernels compile).
  *
  * MG_LIBM_CONTRACT selects whether `a*b+c` is one fused op or two rounded ops.
@@ -191,58 +205,6 @@ MG_HD void mg_sincosf_0_7(float y, float* sinp, float* cosp)
     x = MG_DFMA(-(double)n, MG_HPI, x);
     double s = ((n & 3) == 1 || (n & 3) == 2) ? -1.0 : 1.0;
     mg_sincos_poly(MG_DMUL(x, s), MG_DMUL(x, x), (n & 2) != 0, n, sinp, cosp);
-}
-
-/* ---- logf ------------------------------------------------------------------ */
-#define MG_LOGF_TAB_INIT { \
-    {0x1.661ec79f8f3bep+0, -0x1.57bf7808caadep-2}, {0x1.571ed4aaf883dp+0, -0x1.2bef0a7c06ddbp-2}, \
-    {0x1.49539f0f010bp+0, -0x1.01eae7f513a67p-2},  {0x1.3c995b0b80385p+0, -0x1.b31d8a68224e9p-3}, \
-    {0x1.30d190c8864a5p+0, -0x1.6574f0ac07758p-3}, {0x1.25e227b0b8eap+0, -0x1.1aa2bc79c81p-3}, \
-    {0x1.1bb4a4a1a343fp+0, -0x1.a4e76ce8c0e5ep-4}, {0x1.12358f08ae5bap+0, -0x1.1973c5a611cccp-4}, \
-    {0x1.0953f419900a7p+0, -0x1.252f438e10c1ep-5}, {0x1p+0, 0x0p+0}, \
-    {0x1.e608cfd9a47acp-1, 0x1.aa5aa5df25984p-5},  {0x1.ca4b31f026aap-1, 0x1.c5e53aa362eb4p-4}, \
-    {0x1.b2036576afce6p-1, 0x1.526e57720db08p-3},  {0x1.9c2d163a1aa2dp-1, 0x1.bc2860d22477p-3}, \
-    {0x1.886e6037841edp-1, 0x1.1058bc8a07ee1p-2},  {0x1.767dcf5534862p-1, 0x1.4043057b6ee09p-2}}
-static const double mg_logf_tab[16][2] = MG_LOGF_TAB_INIT;
-#if defined(__CUDACC__)
-static __device__ const double mg_logf_tab_dev[16][2] = MG_LOGF_TAB_INIT;
-#endif
-#if defined(__CUDA_ARCH__)
-#define MG_LOGF_TAB mg_logf_tab_dev
-#else
-#define MG_LOGF_TAB mg_logf_tab
-#endif
-
-#define MG_LN2 0x1.62e42fefa39efp-1
-#define MG_LA0 (-0x1.00ea348b88334p-2)
-#define MG_LA1 0x1.5575b0be00b6ap-2
-#define MG_LA2 (-0x1.ffffef20a4123p-2)
-
-/* logf for finite x > 0 (the only domain the Box-Muller stage feeds it). */
-MG_HD float mg_logf_pos(float x)
-{
-    uint32_t ix = MG_ASUINT(x);
-    if (ix == 0x3f800000u) return 0.0f;
-    if (ix - 0x00800000u >= 0x7f800000u - 0x00800000u) {
-        /* subnormal (callers never pass 0, negatives, inf or nan) */
-        ix = MG_ASUINT(x * 0x1p23f);
-        ix -= 23u << 23;
-    }
-    uint32_t tmp = ix - 0x3f330000u;
-    int i = (int)((tmp >> 19) & 15u);
-    int k = (int32_t)tmp >> 23;
-    uint32_t iz = ix - (tmp & (0x1ffu << 23));
-    double invc = MG_LOGF_TAB[i][0];
-    double logc = MG_LOGF_TAB[i][1];
-    double z = (double)MG_ASFLOAT(iz);
-
-    double r = MG_DFMA(z, invc, -1.0);
-    double y0 = MG_DFMA((double)k, MG_LN2, logc);
-    double r2 = MG_DMUL(r, r);
-    double y = MG_DFMA(MG_LA1, r, MG_LA2);
-    y = MG_DFMA(MG_LA0, r2, y);
-    y = MG_DFMA(y, r2, MG_DADD(y0, r));
-    return (float)y;
 }
 
 /* ---- atanf / atan2f ---------------------------------------------------------

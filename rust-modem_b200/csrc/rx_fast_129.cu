@@ -3,13 +3,16 @@
 #include "launch.h"
 #include "rx_fast.cuh"
 
-/* measured on B200 at C3 (profiles/r01_c3_variants.txt): 64 threads, R = 4, 10 CTAs/SM (96 registers) with 32 TMEM
- * columns beats the 64-tap kernel's shape (8 CTAs/SM at 128 registers) by 3.5 % */
+/* CTA shape, measured on B200 at C3 after the round-2 rework of phases A and C (profiles/r02_c3_variants.txt): 64 threads,
+ * R = 4, 8 CTAs/SM at 128 registers with 64 TMEM columns = 2.66 ms; 10 CTAs/SM at 96 registers (small spills) with 32
+ * columns = 2.73 ms (round 1's choice, then 3.5 % ahead); 128-thread CTAs 2.95-2.99 ms.  The kernel sits at 74 % FMA-pipe
+ * utilisation (profiles/r02_c3_rx129_ncu.txt): it is bound by the two rounded operations per tap the reference's MAC
+ * consists of, not by memory. */
 #ifndef RX129_THREADS
 #define RX129_THREADS 64
-#define RX129_MINB 10
+#define RX129_MINB 8
 #define RX129_R 4
-#define RX129_TMC 32
+#define RX129_TMC 64
 #endif
 
 namespace mg {

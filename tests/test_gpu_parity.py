@@ -533,6 +533,88 @@ def test_full_size_c2_properties(pkg, orc):
     assert np.array_equal(d_sym[idx].cpu().numpy(), sym_ref)
 
 
+def test_full_size_c3_properties(pkg, orc):
+    """BASELINE config 3 at full size: 16384 frames x 65536 samples = 2^30 samples (an 8 GiB sample buffer: every byte
+    offset beyond 2^32), 129-tap RRC both sides.  Round trip without a bit error over all 2.1e9 decided bits, symbol
+    packing, and sampled frames -- the first, the last, and the ones either side of the 2^32-byte boundaries of the
+    sample buffer -- against the oracle, samples bit for bit."""
+    import torch
+
+    F, nsym = 16384, 8192
+    kw = path_kwargs("qpsk", sps=8, shaped=True)
+    m, o = make(pkg, orc, **kw)
+    m.set_stream(torch.cuda.current_stream().cuda_stream)
+    g = torch.Generator(device="cuda").manual_seed(4321)
+    d_bits = torch.randint(0, 2, (F, 2 * nsym), dtype=torch.uint8, device="cuda", generator=g)
+    L = m.frame_samples(2 * nsym)
+    K = m.decided_symbols(L)
+    assert (L, K) == (65536, 8176)
+    d_tx = torch.empty((F, L, 2), dtype=torch.float32, device="cuda")
+    d_sym = torch.empty((F, K), dtype=torch.uint8, device="cuda")
+    d_out = torch.empty((F, K * 2), dtype=torch.uint8, device="cuda")
+    d_cnt = torch.zeros(2, dtype=torch.int64, device="cuda")
+    m.loopback_device_into(d_bits, F, 2 * nsym, d_cnt, tx=d_tx, sym=d_sym, bits_out=d_out)
+    torch.cuda.synchronize()
+    assert tuple(d_cnt.tolist()) == (0, F * K * 2)
+    assert torch.equal(d_out, d_bits[:, : 2 * K])
+    assert torch.equal(d_sym, d_out[:, 0::2] * 2 + d_out[:, 1::2])
+    per4g = (1 << 32) // (L * 8)  # frames per 4 GiB of samples: 8192
+    idx = [0, 1, per4g - 1, per4g, per4g + 1, 2 * per4g - 1, F - 2, F - 1][:7] + [F - 1]
+    idx = sorted(set(idx))
+    bits_s = d_bits[idx].cpu().numpy()
+    tx_ref = o.modulate(bits_s)
+    assert_buffers(d_tx[idx].cpu().numpy(), tx_ref, "C3 sampled tx")
+    _, sym_ref, _ = o.demodulate(tx_ref, want_filt=False)
+    assert np.array_equal(d_sym[idx].cpu().numpy(), sym_ref)
+
+
+def test_full_size_c5_bank_properties(pkg, orc):
+    """BASELINE config 5 as one GPU carries it: 128 carriers x 32 frames x 65536 samples (frames grouped by channel,
+    frames_per_block dividing the channel size), through the fused loopback kernel and through TX + RX: round trip without
+    a bit error, both forms byte-identical, and sampled frames of sampled channels (first, last, channel boundaries)
+    against an oracle configured for that channel's carrier."""
+    import torch
+
+    n_ch, fpc, nsym = 128, 32, 8192
+    F = n_ch * fpc
+    kw = path_kwargs("qpsk", sps=8)
+    hz = [1000 + (3000 * (896 + c)) // 1024 for c in range(n_ch)]  # the carriers rank 7 of 8 carries in bench.py
+    res = {}
+    g = torch.Generator(device="cuda").manual_seed(55)
+    d_bits = torch.randint(0, 2, (F, 2 * nsym), dtype=torch.uint8, device="cuda", generator=g)
+    for form in ("fused", "two kernels"):
+        m = pkg.Modem(**kw)
+        m.set_stream(torch.cuda.current_stream().cuda_stream)
+        m.set_channels([pkg.sample_freq(h, 10000) for h in hz], fpc)
+        L = m.frame_samples(2 * nsym)
+        K = m.decided_symbols(L)
+        d_tx = torch.empty((F, L, 2), dtype=torch.float32, device="cuda")
+        d_sym = torch.empty((F, K), dtype=torch.uint8, device="cuda")
+        d_out = torch.empty((F, K * 2), dtype=torch.uint8, device="cuda")
+        d_cnt = torch.zeros(2, dtype=torch.int64, device="cuda")
+        n0 = m.launch_count
+        if form == "fused":
+            m.loopback_device_into(d_bits, F, 2 * nsym, d_cnt, tx=d_tx, sym=d_sym, bits_out=d_out)
+        else:
+            m.modulate_into(d_bits, F, 2 * nsym, tx=d_tx)
+            m.demodulate_count_into(d_tx, F, L, d_bits, 2 * nsym, d_cnt, sym=d_sym, bits=d_out)
+        torch.cuda.synchronize()
+        assert m.launch_count - n0 == (2 if form == "fused" else 3)  # + the NCO table (128 rows)
+        assert tuple(d_cnt.tolist()) == (0, F * K * 2), form
+        assert torch.equal(d_out, d_bits[:, : 2 * K])
+        res[form] = (d_tx, d_sym)
+        m.close()
+    assert torch.equal(res["fused"][0].view(torch.int32), res["two kernels"][0].view(torch.int32))
+    assert torch.equal(res["fused"][1], res["two kernels"][1])
+    for c in (0, 1, 63, 127):
+        oc = orc.OraclePath(**dict(kw, carrier_hz=hz[c]))
+        rows = [c * fpc, c * fpc + fpc - 1]
+        tx_ref = oc.modulate(d_bits[rows].cpu().numpy())
+        assert_buffers(res["fused"][0][rows].cpu().numpy(), tx_ref, f"C5 channel {c} tx")
+        _, sym_ref, _ = oc.demodulate(tx_ref, want_filt=False)
+        assert np.array_equal(res["fused"][1][rows].cpu().numpy(), sym_ref), c
+
+
 # ----------------------------------------------------------------------------- fused loopback kernel
 def _device_loopback(pkg, m, bits, want_sym=True, want_bits=True, want_tx=True):
     import torch

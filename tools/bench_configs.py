@@ -34,7 +34,7 @@ def run(name, F, shaped, flags=0, sigma_db=None, channels=0, steps=5, sps=8):
     st = torch.cuda.current_stream()
     m.set_stream(st.cuda_stream)
     if channels:
-        m.set_channels([pkg.sample_freq(1100 + 3 * c, 10000) for c in range(channels)], F // channels)
+        m.set_channels([pkg.sample_freq(1000 + (3000 * c) // 1024, 10000) for c in range(channels)], F // channels)
     K = m.decided_symbols(L)
     gen = torch.Generator(device="cuda").manual_seed(1)
     bits = torch.randint(0, 2, (F, NBITS), dtype=torch.uint8, device="cuda", generator=gen)
@@ -71,7 +71,7 @@ if __name__ == "__main__":
     which = sys.argv[1:] or ["c2", "c2f", "c3", "c3f", "c2n", "c3n", "c5"]
     FUSED = pkg.FLAG_FUSED_MAC
     for w in which:
-        if w == "c1": run("C1 rates (sr 10000 / baud 220 -> sps 45, 1000 Hz), 4096 frames x 65520 samples, generic kernels", 4096, False, sps=45)
+        if w == "c1": run("C1 rates (sr 10000 / baud 220 -> sps 45, 1000 Hz), 4096 frames x 65520 samples (tx_rect_fast + rx_dec kernels)", 4096, False, sps=45)
         if w == "c2": run("C2 rect+lp64 exact", 4096, False)
         if w == "c2f": run("C2 rect+lp64 fused-MAC", 4096, False, flags=FUSED)
         if w == "c3": run("C3 rrc129 exact (16384 frames = 2^30 samples)", 16384, True, steps=3)
