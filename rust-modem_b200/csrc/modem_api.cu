@@ -106,7 +106,7 @@ struct modem_ctx {
     bool force_generic = false;
     bool pipe_trace = false; /* MODEM_GPU_PIPE_TRACE=1: per-chunk event timeline of the host-buffer pipeline on stderr */
     bool pipe_fused = false; /* MODEM_GPU_PIPE_FUSED=1: the host-buffer pipeline runs the fused loopback kernel per chunk instead of TX + RX (measured slower, see loopback_pipelined) */
-    bool pipe_ramp = false; /* MODEM_GPU_PIPE_RAMP=1: short chunks at both ends of the call (measured slower with TX + RX, a wash with the fused kernel) */
+    int pipe_ramp = 0; /* MODEM_GPU_PIPE_RAMP: 1 = doubling chunks at both ends of the call, n >= 2 = one chunk of 1/n at each end (all measured slower or equal) */
     bool no_rx_dec = false; /* MODEM_GPU_NO_RX_DEC=1: shapes of the tuned any-sps RX kernel (rx_dec.cu) take the generic kernel */
     bool no_sign_slice = false; /* MODEM_GPU_NO_SIGN_SLICE=1: the fast RX kernel always runs the nearest-point search */
     bool no_fused_loop = false; /* MODEM_GPU_NO_FUSED_LOOP=1: the loopback entries run the TX and the RX kernel separately */
@@ -864,7 +864,7 @@ int modem_gpu_create(modem_ctx_t** out, int device, const modem_cfg_t* cfg)
     const char* pf = getenv("MODEM_GPU_PIPE_FUSED");
     ctx->pipe_fused = pf && pf[0] == '1';
     const char* pr = getenv("MODEM_GPU_PIPE_RAMP");
-    ctx->pipe_ramp = pr && pr[0] == '1';
+    ctx->pipe_ramp = pr ? atoi(pr) : 0;
     const char* ptr = getenv("MODEM_GPU_PIPE_TRACE");
     ctx->pipe_trace = ptr && ptr[0] == '1';
     const char* nf = getenv("MODEM_GPU_NO_FUSED_LOOP");
@@ -1291,8 +1291,9 @@ int loopback_pipelined(modem_ctx* ctx, const uint8_t* bits, size_t F, size_t nbi
     {
         const size_t unit = ctx->n_channels ? std::min(Fc, ctx->frames_per_channel) : 1; /* chunk edges stay on what Fc was aligned to */
         std::vector<size_t> head;
-        if (ctx->pipe_ramp && !ctx->n_channels)
+        if (ctx->pipe_ramp == 1 && !ctx->n_channels)
             for (size_t n = std::max<size_t>(Fc / 8, 16); n < Fc; n *= 2) head.push_back(n);
+        if (ctx->pipe_ramp >= 2 && !ctx->n_channels && Fc / (size_t)ctx->pipe_ramp >= 8) head.push_back(Fc / (size_t)ctx->pipe_ramp); /* one short chunk at each end */
         size_t ramp = 0;
         for (size_t n : head) ramp += n;
         if (2 * ramp + Fc > F) head.clear(), ramp = 0;
