@@ -6,12 +6,19 @@
  * CTA shape (measured on B200 at C2, profiles/r02_fused_variants.txt): 128 threads x 4 symbols per thread, 4 CTAs per SM
  * (16 warps), 64 TMEM columns per CTA -- 256 of the SM's 512 columns, on all 128 lanes.  64-thread CTAs at 8 per SM use
  * all 512 columns for the same speed; more CTAs with 32 columns and fewer registers are 5-10 % slower; 8 symbols per
- * thread (less FIR shared traffic) needs > 150 registers and is 2x slower. */
+ * thread (32 % less FIR shared traffic) needs 150-170 registers, i.e. 12 warps per SM: 0.62 ms at best (FUSED_R etc. below
+ * rebuild that shape). */
 #include "launch.h"
 #include "rx_fast.cuh"
 
 namespace mg {
-constexpr int kFusedThreads = 128, kFusedMinB = 4, kFusedR = 4, kFusedTmc = 64;
+#ifndef FUSED_R
+#define FUSED_R 4
+#define FUSED_THREADS 128
+#define FUSED_MINB 4
+#define FUSED_TMC 64
+#endif
+constexpr int kFusedThreads = FUSED_THREADS, kFusedMinB = FUSED_MINB, kFusedR = FUSED_R, kFusedTmc = FUSED_TMC;
 uint64_t loop_fused_tile_symbols_64() { return (uint64_t)kFusedThreads * kFusedR; }
 /* samples the tiles of a frame reach: the last tile ends at tiles*TS*8 + delay + OFF - 7 (OFF = 0, odd delay) */
 bool loop_fused_supported_64(const RxArgs& a)

@@ -235,11 +235,14 @@ __global__ void __launch_bounds__(THREADS, MINB)
     for (int r = 0; r < R; ++r) toff[r] = (uint32_t)((ka + r) % a.n_tables) * a.n_const;
     const bool have_any = ka < a.K, have_all = ka + R <= a.K;
     /* vector emit: every frame's symbol row must start on a multiple of R symbols */
-    const bool vec_out = a.bps == 2 && have_all && (a.K % R == 0) &&
-                         ((reinterpret_cast<uintptr_t>(a.sym) % R) == 0) &&
-                         ((reinterpret_cast<uintptr_t>(a.bits) % (2 * R)) == 0);
-    const bool ref_vec = a.ref_bits && vec_out && (a.ref_stride % (2 * R) == 0) &&
-                         ((reinterpret_cast<uintptr_t>(a.ref_bits) % (2 * R)) == 0);
+    /* vector emit: every frame's symbol row must start on a multiple of VG symbols (R = 8 emits two groups of 4, so that
+     * K = 8188 symbols per frame -- a multiple of 4, not of 8 -- still takes the vector path) */
+    constexpr int VG = R == 8 ? 4 : R;
+    const bool vec_out = a.bps == 2 && have_all && (a.K % VG == 0) &&
+                         ((reinterpret_cast<uintptr_t>(a.sym) % VG) == 0) &&
+                         ((reinterpret_cast<uintptr_t>(a.bits) % (2 * VG)) == 0);
+    const bool ref_vec = a.ref_bits && vec_out && (a.ref_stride % (2 * VG) == 0) &&
+                         ((reinterpret_cast<uintptr_t>(a.ref_bits) % (2 * VG)) == 0);
 
     /* one 4-point table for every symbol: keep it in registers */
     const bool lut4 = a.n_const == 4 && a.n_tables == 1;
@@ -295,15 +298,18 @@ __global__ void __launch_bounds__(THREADS, MINB)
      * arithmetic.  (Round 1: 2-byte loads and select/sign logic per CHUNK, 8 instructions x 17 chunks per thread and
      * frame.)  Rows start on 8-byte boundaries (the launcher checks). */
     constexpr int BWORDS = (2 * C::NBLK + 7 + 7) / 8;
-    static_assert(!TXF || BWORDS <= 2 * THREADS, "two words per thread at most");
+    static_assert(!TXF || BWORDS <= 3 * THREADS, "three words per thread at most");
+    constexpr bool W3 = TXF && BWORDS > 2 * THREADS; /* a few threads carry a third word (R = 8 shapes) */
     __shared__ __align__(16) f32x2 s_sq[TXF ? 4 * BWORDS : 2];
     const long long brow0 = (2 * (nbase >> 3)) & ~7ll; /* row byte offset of table entry 0; negative in the first tile */
     /* this thread's first chunk lies in symbol (nbase + 2*tid) >> 3; chunk it*THREADS + tid: THREADS/4 symbols on per step */
     const int sqoff = TXF ? (int)(((nbase + 2 * (long long)tid) >> 3) - (brow0 >> 1)) : 0;
     const uint8_t* brow = TXF ? a.ref_bits + f0 * a.ref_stride : nullptr;
     float4* txrow = TXF ? reinterpret_cast<float4*>(a.tx_out + f0 * a.L + nbase) + tid : nullptr;
-    unsigned long long nb0 = 0, nb1 = 0;
-    const long long bo0 = brow0 + 8 * tid, bo1 = bo0 + 8 * THREADS;
+    unsigned long long nb0 = 0, nb1 = 0, nb2 = 0;
+    const long long bo0 = brow0 + 8 * tid, bo1 = bo0 + 8 * THREADS, bo2 = bo1 + 8 * THREADS;
+    const bool bw2 = W3 && tid + 2 * THREADS < BWORDS;
+    const bool bv2 = bw2 && bo2 >= 0 && bo2 + 8 <= (long long)a.ref_stride;
     const bool bw0 = TXF && tid < BWORDS, bw1 = TXF && tid + THREADS < BWORDS; /* has a first / second word slot */
     const bool bv0 = bw0 && bo0 >= 0 && bo0 + 8 <= (long long)a.ref_stride;     /* ... and it lies inside the row */
     const bool bv1 = bw1 && bo1 >= 0 && bo1 + 8 <= (long long)a.ref_stride;
@@ -311,6 +317,10 @@ __global__ void __launch_bounds__(THREADS, MINB)
         nb0 = nb1 = 0; /* symbols outside the frame map to entry 0: finite, and multiplied by the NCO table's zeros */
         if (bv0) nb0 = __ldg(reinterpret_cast<const unsigned long long*>(row + bo0));
         if (bv1) nb1 = __ldg(reinterpret_cast<const unsigned long long*>(row + bo1));
+        if (W3) {
+            nb2 = 0;
+            if (bv2) nb2 = __ldg(reinterpret_cast<const unsigned long long*>(row + bo2));
+        }
     };
     auto map_word = [&](unsigned long long w, f32x2* dst) {
         f32x2 e[4];
@@ -326,6 +336,7 @@ __global__ void __launch_bounds__(THREADS, MINB)
     auto park_bits = [&]() {
         if (bw0) map_word(nb0, s_sq + (TXF ? 4 * tid : 0));
         if (bw1) map_word(nb1, s_sq + (TXF ? 4 * (tid + THREADS) : 0));
+        if (W3 && bw2) map_word(nb2, s_sq + (W3 ? 4 * (tid + 2 * THREADS) : 0));
     };
     if (TXF && f0 < f1) {
         fetch_bits(brow);
@@ -392,7 +403,7 @@ __global__ void __launch_bounds__(THREADS, MINB)
                         }
                     }
                 };
-                static_assert(C::ITER <= 8 * G, "one switch case per trip");
+                static_assert(!NOISE || C::ITER <= 8 * G, "one switch case per trip");
                 switch (it0 / G) {
                 case 0: apply(std::integral_constant<int, 0>{}); break;
                 case 1: apply(std::integral_constant<int, 1>{}); break;
@@ -474,8 +485,8 @@ __global__ void __launch_bounds__(THREADS, MINB)
         uint32_t refw[4] = {0u, 0u, 0u, 0u}; /* 2R reference bits, one byte each */
         if (ref_vec) {
             if (R == 8) {
-                const uint4 t = __ldg(reinterpret_cast<const uint4*>(refp));
-                refw[0] = t.x; refw[1] = t.y; refw[2] = t.z; refw[3] = t.w;
+                const uint2 t = __ldg(reinterpret_cast<const uint2*>(refp)), u = __ldg(reinterpret_cast<const uint2*>(refp) + 1);
+                refw[0] = t.x; refw[1] = t.y; refw[2] = u.x; refw[3] = u.y;
             } else if (R == 4) {
                 const uint2 t = __ldg(reinterpret_cast<const uint2*>(refp));
                 refw[0] = t.x; refw[1] = t.y;
@@ -579,12 +590,18 @@ __global__ void __launch_bounds__(THREADS, MINB)
                 if (a.soft) a.soft[orow + r] = make_float2(I[r], Q[r]);
             }
             if (a.sym) {
-                if (R == 8) *reinterpret_cast<uint2*>(a.sym + orow) = make_uint2(symw[0], symw[1]);
+                if (R == 8) {
+                    reinterpret_cast<uint32_t*>(a.sym + orow)[0] = symw[0];
+                    reinterpret_cast<uint32_t*>(a.sym + orow)[1] = symw[1];
+                }
                 else if (R == 4) *reinterpret_cast<uint32_t*>(a.sym + orow) = symw[0];
                 else *reinterpret_cast<uint16_t*>(a.sym + orow) = (uint16_t)symw[0];
             }
             if (a.bits) {
-                if (R == 8) *reinterpret_cast<uint4*>(a.bits + 2 * orow) = make_uint4(bitw[0], bitw[1], bitw[2], bitw[3]);
+                if (R == 8) {
+                    reinterpret_cast<uint2*>(a.bits + 2 * orow)[0] = make_uint2(bitw[0], bitw[1]);
+                    reinterpret_cast<uint2*>(a.bits + 2 * orow)[1] = make_uint2(bitw[2], bitw[3]);
+                }
                 else if (R == 4) *reinterpret_cast<uint2*>(a.bits + 2 * orow) = make_uint2(bitw[0], bitw[1]);
                 else *reinterpret_cast<uint32_t*>(a.bits + 2 * orow) = bitw[0];
             }
