@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define MODEM_GPU_ABI_VERSION 3
+#define MODEM_GPU_ABI_VERSION 4
 
 enum {
     MODEM_OK = 0,
@@ -283,6 +283,19 @@ int modem_gpu_loopback_device(modem_ctx_t* ctx, const uint8_t* bits, size_t F, s
 int modem_gpu_loopback(modem_ctx_t* ctx, const uint8_t* bits, size_t F, size_t nbits,
                        float sigma, uint64_t seed, uint64_t frame0, modem_c32_t* tx,
                        uint8_t* sym, uint8_t* bits_out, uint64_t counters[2]);
+
+/* loopback_packed (extension; NOT the reference's payload format): modem_gpu_loopback on PACKED payloads.
+ *   packed     [F][ceil(nbits/8)]   bit j of a frame = bit 7 - j%8 of byte j/8 (first bit = most significant, the order of
+ *                                   digital/util.rs:5-11); pad bits of a row's last byte are ignored
+ *   packed_out [F][ceil(K*bps/8)]   (nullable) the demapped bits in the same packing, pad bits zero
+ * The reference's bit sources carry one BYTE per bit (data.rs:35-40, AsciiBits of modulate.rs:98); with host buffers that
+ * format makes modem_gpu_loopback a PCIe copy.  This entry moves 1/8 of the bytes: the rows are
+ * unpacked / packed on the device either side of the same kernels, so decisions and counters equal modem_gpu_loopback's
+ * on the unpacked bits.  Host or device pointers (host: chunked copy-in / kernels / copy-out pipeline,
+ * MODEM_GPU_PACKED_CHUNK frames per chunk); counters is a host pointer, the call synchronises. */
+int modem_gpu_loopback_packed(modem_ctx_t* ctx, const uint8_t* packed, size_t F, size_t nbits,
+                              float sigma, uint64_t seed, uint64_t frame0, uint8_t* packed_out,
+                              uint64_t counters[2]);
 
 /* ------------------------------------------------------------------ memory helpers */
 int modem_gpu_malloc(modem_ctx_t* ctx, void** dptr, size_t bytes);

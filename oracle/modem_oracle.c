@@ -727,6 +727,21 @@ void orc_random_bits(uint8_t* bits, size_t F, size_t nbits, uint64_t seed, uint6
     }
 }
 
+void orc_unpack_bits(const uint8_t* packed, uint8_t* bits, size_t F, size_t nbits)
+{
+    const size_t pb = (nbits + 7) / 8;
+    for (size_t f = 0; f < F; ++f)
+        for (size_t j = 0; j < nbits; ++j) bits[f * nbits + j] = (uint8_t)((packed[f * pb + j / 8] >> (7 - j % 8)) & 1u);
+}
+void orc_pack_bits(const uint8_t* bits, uint8_t* packed, size_t F, size_t nbits)
+{
+    const size_t pb = (nbits + 7) / 8;
+    for (size_t f = 0; f < F; ++f) {
+        for (size_t b = 0; b < pb; ++b) packed[f * pb + b] = 0;
+        for (size_t j = 0; j < nbits; ++j) packed[f * pb + j / 8] |= (uint8_t)((bits[f * nbits + j] & 1u) << (7 - j % 8));
+    }
+}
+
 float orc_sigma_for_ebn0(const float* const_iq, size_t n_points, size_t bps, float slicer_gain,
                          float rx_gain, const float* rx_taps, size_t n_rx, double ebn0_db)
 {

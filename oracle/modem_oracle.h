@@ -220,6 +220,13 @@ void orc_awgn(float* buf /*[F][L][2]*/, size_t F, size_t L, float sigma, uint64_
  * block with key = (s lo, s hi ^ 0x62697473) and counter = (j/128 lo, j/128 hi, g lo, g hi); one byte (0/1) per bit. */
 void orc_random_bits(uint8_t* bits /*[F][nbits]*/, size_t F, size_t nbits, uint64_t seed, uint64_t frame0);
 
+/* ---- packed payload (extension, modem_gpu_loopback_packed): rows of ceil(nbits/8) bytes; bit j of a frame = bit 7 - j%8 of
+ * byte j/8 (first bit most significant: the order in which bytes_to_bits, digital/util.rs:5-11, packs a symbol); pad bits
+ * of a row's last byte are written as zero and ignored on input.  unpack yields the one-byte-per-bit rows of
+ * data.rs:35-40, pack is its inverse on bit 0 of every byte. */
+void orc_unpack_bits(const uint8_t* packed /*[F][ceil(nbits/8)]*/, uint8_t* bits /*[F][nbits]*/, size_t F, size_t nbits);
+void orc_pack_bits(const uint8_t* bits /*[F][nbits]*/, uint8_t* packed /*[F][ceil(nbits/8)]*/, size_t F, size_t nbits);
+
 /* Es = mean |c|^2 of the scheme's constellation; sigma for a given Eb/N0 so that the
  * slicer sees the textbook SNR (DESIGN.md "AWGN scaling"). */
 float orc_sigma_for_ebn0(const float* const_iq, size_t n_points, size_t bps, float slicer_gain,

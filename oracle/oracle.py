@@ -128,6 +128,8 @@ def lib():
         L.orc_box_muller.argtypes = [C.c_uint32, C.c_uint32, f32p, f32p]
         L.orc_awgn.argtypes = [f32p, sz, sz, f32, C.c_uint64, C.c_uint64]
         L.orc_random_bits.argtypes = [u8p, sz, sz, C.c_uint64, C.c_uint64]
+        L.orc_unpack_bits.argtypes = [u8p, u8p, sz, sz]
+        L.orc_pack_bits.argtypes = [u8p, u8p, sz, sz]
         L.orc_sigma_for_ebn0.restype = f32
         L.orc_sigma_for_ebn0.argtypes = [f32p, sz, sz, f32, f32, f32p, sz, C.c_double]
         PA = C.POINTER(Path)
@@ -177,6 +179,24 @@ def random_bits(F, nbits, seed, frame0=0):
     """Philox payload bits (extension, modem_oracle.h): [F][nbits] bytes 0/1."""
     out = np.zeros((F, nbits), np.uint8)
     lib().orc_random_bits(_u8p(out), F, nbits, seed, frame0)
+    return out
+
+
+def unpack_bits(packed, nbits):
+    """Packed payload rows (extension, modem_oracle.h) -> [F][nbits] bytes 0/1."""
+    packed = np.ascontiguousarray(packed, np.uint8)
+    assert packed.shape[1] == (nbits + 7) // 8
+    out = np.zeros((packed.shape[0], nbits), np.uint8)
+    lib().orc_unpack_bits(_u8p(packed), _u8p(out), packed.shape[0], nbits)
+    return out
+
+
+def pack_bits(bits):
+    """[F][nbits] bytes 0/1 -> packed payload rows [F][ceil(nbits/8)], pad bits zero."""
+    bits = np.ascontiguousarray(bits, np.uint8)
+    F, nbits = bits.shape
+    out = np.zeros((F, (nbits + 7) // 8), np.uint8)
+    lib().orc_pack_bits(_u8p(bits), _u8p(out), F, nbits)
     return out
 
 

@@ -112,6 +112,7 @@ def lib():
     L.modem_gpu_ber_sweep.argtypes = [vp, vp, sz, sz, sz, f32p, u64, u64, vp, vp]
     L.modem_gpu_loopback_device.argtypes = [vp, vp, sz, sz, f32, u64, u64, vp, vp, vp, vp]
     L.modem_gpu_loopback.argtypes = [vp, u8p, sz, sz, f32, u64, u64, vp, vp, vp, C.POINTER(u64)]
+    L.modem_gpu_loopback_packed.argtypes = [vp, u8p, sz, sz, f32, u64, u64, vp, C.POINTER(u64)]
     L.modem_gpu_malloc.argtypes = [vp, C.POINTER(vp), sz]
     L.modem_gpu_free.argtypes = [vp, vp]
     L.modem_gpu_host_alloc.argtypes = [C.POINTER(vp), sz]
@@ -335,6 +336,12 @@ class Modem:
                                           _ptr(bits_out), cnt))
         return cnt[0], cnt[1]
 
+    def loopback_packed_into(self, packed, F, nbits, packed_out=None, sigma=0.0, seed=0, frame0=0):
+        """Extension: the loopback on packed payloads (8 bits per byte, first bit = MSB; np.packbits order)."""
+        cnt = (C.c_uint64 * 2)(0, 0)
+        self._ck(lib().modem_gpu_loopback_packed(self._ctx, _ptr(packed), F, nbits, sigma, seed, frame0, _ptr(packed_out), cnt))
+        return cnt[0], cnt[1]
+
     # -- numpy conveniences (host buffers through the C ABI)
     def modulate(self, bits, want_iq=False):
         bits = np.ascontiguousarray(bits, np.uint8)
@@ -422,6 +429,17 @@ class Modem:
         tx = np.zeros((F, L, 2), np.float32) if want_tx else None
         cnt = self.loopback_into(bits, F, nbits, sigma, seed, frame0, tx, sym, bo)
         return {"sym": sym, "bits": bo, "tx": tx, "errors": cnt[0], "compared": cnt[1]}
+
+
+    def loopback_packed(self, packed, nbits, sigma=0.0, seed=0, frame0=0):
+        """packed [F][ceil(nbits/8)] uint8 -> {'packed': [F][ceil(K*bps/8)], 'errors', 'compared'}."""
+        packed = np.ascontiguousarray(packed, np.uint8)
+        F = packed.shape[0]
+        assert packed.shape[1] == (nbits + 7) // 8
+        K = self.decided_symbols(self.frame_samples(nbits))
+        out = np.zeros((F, (K * self.bps + 7) // 8), np.uint8)
+        cnt = self.loopback_packed_into(packed, F, nbits, out, sigma, seed, frame0)
+        return {"packed": out, "errors": cnt[0], "compared": cnt[1]}
 
 
 class Comm:

@@ -247,6 +247,47 @@ __global__ void __launch_bounds__(kThreads) random_bits_kernel(uint8_t* bits, u6
     }
 }
 
+/* Packed payloads (extension, modem_gpu_loopback_packed; oracle/modem_oracle.h "packed payload"): rows of
+ * ceil(nbits/8) bytes, bit j of a frame = bit 7 - j%8 of byte j/8 (first bit = most significant, the order in which
+ * digital/util.rs:5-11 packs a symbol), pad bits of a row's last byte zero.  One thread = one packed byte = one 8-byte
+ * word of bit bytes (the layout data.rs:35-40 consumes). */
+__global__ void __launch_bounds__(kThreads) unpack_bits_kernel(const uint8_t* __restrict__ packed, uint8_t* __restrict__ bits, u64 F, u64 nbits)
+{
+    const u64 pb = (nbits + 7) / 8, total = F * pb;
+    const bool vec = (nbits % 8 == 0) && ((reinterpret_cast<uintptr_t>(bits) & 7u) == 0);
+    for (u64 g = (u64)blockIdx.x * kThreads + threadIdx.x; g < total; g += (u64)gridDim.x * kThreads) {
+        const u64 f = g / pb, j = g % pb;
+        /* the byte replicated eight times; word byte i keeps bit 7-i of it, then any non-zero byte becomes 1 */
+        unsigned long long w = ((unsigned long long)packed[g] * 0x0101010101010101ull) & 0x0102040810204080ull;
+        w = ((w + 0x7f7f7f7f7f7f7f7full) >> 7) & 0x0101010101010101ull;
+        uint8_t* dst = bits + f * nbits + 8 * j;
+        if (vec) {
+            *reinterpret_cast<unsigned long long*>(dst) = w;
+        } else {
+            const u64 left = nbits - 8 * j;
+            for (u64 i = 0; i < 8 && i < left; ++i) dst[i] = (uint8_t)(w >> (8 * i));
+        }
+    }
+}
+__global__ void __launch_bounds__(kThreads) pack_bits_kernel(const uint8_t* __restrict__ bits, uint8_t* __restrict__ packed, u64 F, u64 nbits)
+{
+    const u64 pb = (nbits + 7) / 8, total = F * pb;
+    const bool vec = (nbits % 8 == 0) && ((reinterpret_cast<uintptr_t>(bits) & 7u) == 0);
+    for (u64 g = (u64)blockIdx.x * kThreads + threadIdx.x; g < total; g += (u64)gridDim.x * kThreads) {
+        const u64 f = g / pb, j = g % pb;
+        const uint8_t* src = bits + f * nbits + 8 * j;
+        unsigned long long w = 0;
+        if (vec) {
+            w = __ldg(reinterpret_cast<const unsigned long long*>(src));
+        } else {
+            const u64 left = nbits - 8 * j;
+            for (u64 i = 0; i < 8 && i < left; ++i) w |= (unsigned long long)src[i] << (8 * i);
+        }
+        /* bit 0 of word byte i lands on bit 63-i of the product: 8i + 9(7-i) = 63 - i, no two terms share a position */
+        packed[g] = (uint8_t)(((w & 0x0101010101010101ull) * 0x8040201008040201ull) >> 56);
+    }
+}
+
 /*
  * Generic decimating RX (any sps / tap count / q_offset): one thread per symbol.
  * dynamic smem: float2 s_cs[R]; float s_vi[RP]; float s_vq[RP]; float s_taps[N]

@@ -76,6 +76,8 @@ struct modem_ctx {
     std::vector<cudaEvent_t> pipe_events; /* 3 per chunk: copied in, computed, copied out (the last only when tracing) */
     cudaEvent_t pipe_t0 = nullptr;
     Scratch pipe_tx; /* one chunk of TX samples (two-kernel form only) */
+    Scratch s_packed_in, s_packed_out; /* modem_gpu_loopback_packed: the call's packed rows on the device (host callers) */
+    size_t packed_chunk = 0; /* MODEM_GPU_PACKED_CHUNK: frames per chunk of the packed-payload pipeline (0 = ~512 MB of samples) */
     bool lanes_ready = false;
     cudaEvent_t ev_start = nullptr;
     u64 frame_base = 0; /* see ChannelView::frame_base */
@@ -879,6 +881,8 @@ int modem_gpu_create(modem_ctx_t** out, int device, const modem_cfg_t* cfg)
     ctx->rx_tile_major = tm ? atoi(tm) : -1;
     const char* pc = getenv("MODEM_GPU_PIPE_CHUNK");
     ctx->pipe_chunk = pc ? (size_t)atoll(pc) : 0;
+    const char* pkc = getenv("MODEM_GPU_PACKED_CHUNK");
+    if (pkc && atoll(pkc) > 0) ctx->packed_chunk = (size_t)atoll(pkc);
     const char* lc = getenv("MODEM_GPU_LOOP_CHUNK");
     ctx->loop_chunk = lc ? (size_t)atoll(lc) : 0;
     const char* ng = getenv("MODEM_GPU_NO_GRAPH");
@@ -927,6 +931,8 @@ void modem_gpu_destroy(modem_ctx_t* ctx)
         if (e) cudaEventDestroy(e);
     if (ctx->pipe_t0) cudaEventDestroy(ctx->pipe_t0);
     if (ctx->pipe_tx.p) cudaFree(ctx->pipe_tx.p);
+    if (ctx->s_packed_in.p) cudaFree(ctx->s_packed_in.p);
+    if (ctx->s_packed_out.p) cudaFree(ctx->s_packed_out.p);
     if (ctx->ev_start) cudaEventDestroy(ctx->ev_start);
     for (auto e : ctx->ev_pool)
         if (e) cudaEventDestroy(e);
@@ -1625,6 +1631,141 @@ int modem_gpu_loopback(modem_ctx_t* ctx, const uint8_t* bits, size_t F, size_t n
     u64 h[2] = {0, 0};
     CK(ctx, cudaMemcpyAsync(h, ctx->d_counters, sizeof h, cudaMemcpyDeviceToHost, ctx->stream));
     CK(ctx, cudaStreamSynchronize(ctx->stream));
+    if (counters) {
+        counters[0] += h[0];
+        counters[1] += h[1];
+    }
+    return MODEM_OK;
+}
+
+/*
+ * loopback_packed (extension): the loopback on PACKED payloads, 8 bits per byte in each direction instead of the
+ * reference's one byte per bit (data.rs:35-40) -- 1/8 of the bytes over PCIe, which is what bounds modem_gpu_loopback with
+ * host buffers.  Per chunk of frames: copy-in (host callers), unpack_bits_kernel into the byte-per-bit rows the path
+ * consumes, the loopback kernels (the fused kernel WITHOUT a sample buffer when the shape allows, else TX + RX through a
+ * chunk-sized one), pack_bits_kernel, copy-out; three streams by role as in loopback_pipelined.  Device callers run the
+ * same sequence in place, one chunk, no copies.  The bit decisions are those of modem_gpu_loopback, bit for bit.
+ */
+int modem_gpu_loopback_packed(modem_ctx_t* ctx, const uint8_t* packed, size_t F, size_t nbits, float sigma, uint64_t seed,
+                              uint64_t frame0, uint8_t* packed_out, uint64_t counters[2])
+{
+    if (!ctx || (!packed && F && nbits)) return fail(ctx, MODEM_ERR_INVALID, "loopback_packed: null argument");
+    CK(ctx, cudaSetDevice(ctx->device));
+    if (ctx->n_channels && F > ctx->n_channels * ctx->frames_per_channel)
+        return fail(ctx, MODEM_ERR_INVALID, "loopback_packed: more frames than channels * frames_per_channel");
+    const size_t L = modem_gpu_frame_samples(ctx, nbits);
+    const size_t K = modem_gpu_decided_symbols(ctx, L);
+    const size_t bps = ctx->cfg.bits_per_symbol;
+    const size_t nout = K * bps, PB = (nbits + 7) / 8, OB = (nout + 7) / 8;
+    if (F == 0 || L == 0) return MODEM_OK;
+    const bool dev_in = is_device_ptr(packed), dev_out = packed_out && is_device_ptr(packed_out);
+    const bool copy_in = !dev_in, copy_out = packed_out && !dev_out && OB;
+    size_t Fc = F;
+    if (copy_in || copy_out) {
+        Fc = ctx->packed_chunk ? ctx->packed_chunk : std::max<size_t>(1, ((size_t)512 << 20) / (L * sizeof(float2)));
+        if (ctx->n_channels) { /* chunk boundaries on channel boundaries (or whole divisors of them) */
+            const size_t fc = ctx->frames_per_channel;
+            if (Fc >= fc) Fc -= Fc % fc;
+            else while (fc % Fc) --Fc;
+        }
+        Fc = std::min(Fc, F);
+    }
+    const size_t n_chunks = (F + Fc - 1) / Fc;
+    if (!ctx->lanes_ready) {
+        for (auto& ln : ctx->lanes) {
+            CK(ctx, cudaStreamCreateWithFlags(&ln.s, cudaStreamNonBlocking));
+            CK(ctx, cudaEventCreateWithFlags(&ln.done, cudaEventDisableTiming));
+        }
+        CK(ctx, cudaEventCreateWithFlags(&ctx->ev_start, cudaEventDisableTiming));
+        ctx->lanes_ready = true;
+    }
+    while (ctx->pipe_events.size() < 3 * n_chunks) {
+        cudaEvent_t e;
+        CK(ctx, cudaEventCreateWithFlags(&e, ctx->pipe_trace ? cudaEventDefault : cudaEventDisableTiming));
+        ctx->pipe_events.push_back(e);
+    }
+    /* does a chunk run the fused kernel (no sample buffer) or TX + RX (one chunk of samples)? */
+    mg::RxArgs probe{};
+    ctx->frame_base = 0;
+    const bool fused = loop_fused_eligible(ctx, reinterpret_cast<const uint8_t*>(uintptr_t(16)), Fc, nbits, nullptr, sigma, probe);
+    int rc = ensure(ctx, ctx->s_bits, F * nbits);
+    if (!rc && packed_out) rc = ensure(ctx, ctx->s_bits_out, F * nout);
+    if (!rc && copy_in) rc = ensure(ctx, ctx->s_packed_in, F * PB);
+    if (!rc && copy_out) rc = ensure(ctx, ctx->s_packed_out, F * OB);
+    if (!rc && !fused) rc = ensure(ctx, ctx->pipe_tx, Fc * L * sizeof(float2));
+    if (rc) return rc;
+    uint8_t* d_bits = (uint8_t*)ctx->s_bits.p;
+    uint8_t* d_out = packed_out ? (uint8_t*)ctx->s_bits_out.p : nullptr;
+    const uint8_t* d_pin = copy_in ? (const uint8_t*)ctx->s_packed_in.p : packed;
+    uint8_t* d_pout = copy_out ? (uint8_t*)ctx->s_packed_out.p : packed_out;
+    CK(ctx, cudaMemsetAsync(ctx->d_counters, 0, 2 * sizeof(u64), ctx->stream));
+    {
+        /* NCO tables for the whole call, built once before the streams fork (every chunk shares them) */
+        mg::ChannelView dummy = channel_view(ctx);
+        int rc0 = attach_carrier_table(ctx, dummy, F, L, false);
+        if (rc0) return rc0;
+    }
+    CK(ctx, cudaEventRecord(ctx->ev_start, ctx->stream));
+    for (auto& ln : ctx->lanes) CK(ctx, cudaStreamWaitEvent(ln.s, ctx->ev_start, 0));
+    cudaStream_t user_stream = ctx->stream;
+    cudaStream_t s_in = ctx->lanes[0].s, s_k = ctx->lanes[1].s, s_out = ctx->lanes[2].s;
+    cudaError_t e = cudaSuccess;
+    if (copy_in)
+        for (size_t c = 0; c < n_chunks && e == cudaSuccess; ++c) {
+            const size_t fs = c * Fc, n = std::min(Fc, F - fs);
+            e = cudaMemcpyAsync(const_cast<uint8_t*>(d_pin) + fs * PB, packed + fs * PB, n * PB, cudaMemcpyHostToDevice, s_in);
+            if (e == cudaSuccess) e = cudaEventRecord(ctx->pipe_events[3 * c], s_in);
+        }
+    auto grid_for = [&](u64 total) { return (unsigned)std::min<u64>((total + mg::kThreads - 1) / mg::kThreads, (u64)ctx->sm_count * 32); };
+    for (size_t c = 0; c < n_chunks && !rc && e == cudaSuccess; ++c) {
+        const size_t fs = c * Fc, n = std::min(Fc, F - fs);
+        if (copy_in) e = cudaStreamWaitEvent(s_k, ctx->pipe_events[3 * c], 0);
+        if (e != cudaSuccess) break;
+        mg::unpack_bits_kernel<<<grid_for((u64)n * PB), mg::kThreads, 0, s_k>>>(d_pin + fs * PB, d_bits + fs * nbits, n, nbits);
+        ctx->launches++;
+        ctx->stream = s_k; /* launch_* enqueue on ctx->stream */
+        ctx->frame_base = fs;
+        rc = launch_loop_fused(ctx, d_bits + fs * nbits, n, nbits, nullptr, nullptr, d_out ? d_out + fs * nout : nullptr, ctx->d_counters, sigma);
+        if (rc == 1) {
+            rc = MODEM_OK;
+        } else if (rc == 0) {
+            if (fused) { /* the probe said fused: no sample buffer was reserved */
+                rc = fail(ctx, MODEM_ERR_UNSUPPORTED, "loopback_packed: internal: chunk not eligible for the fused kernel");
+            } else {
+                rc = launch_tx(ctx, d_bits + fs * nbits, n, nbits, (float2*)ctx->pipe_tx.p, nullptr);
+                if (!rc)
+                    rc = launch_rx(ctx, (const float2*)ctx->pipe_tx.p, n, L, nullptr, d_out ? d_out + fs * nout : nullptr, nullptr, nullptr,
+                                   d_bits + fs * nbits, nbits, ctx->d_counters, sigma, seed, frame0 + fs);
+            }
+        }
+        ctx->stream = user_stream;
+        ctx->frame_base = 0;
+        if (rc) break;
+        if (d_pout && OB) {
+            mg::pack_bits_kernel<<<grid_for((u64)n * OB), mg::kThreads, 0, s_k>>>(d_out + fs * nout, d_pout + fs * OB, n, nout);
+            ctx->launches++;
+        }
+        e = cudaGetLastError();
+        if (e == cudaSuccess) e = cudaEventRecord(ctx->pipe_events[3 * c + 1], s_k);
+        if (e == cudaSuccess && copy_out) {
+            e = cudaStreamWaitEvent(s_out, ctx->pipe_events[3 * c + 1], 0);
+            if (e == cudaSuccess) e = cudaMemcpyAsync(packed_out + fs * OB, d_pout + fs * OB, n * OB, cudaMemcpyDeviceToHost, s_out);
+        }
+    }
+    if (e != cudaSuccess && !rc) rc = fail(ctx, MODEM_ERR_CUDA, std::string("loopback_packed: ") + cudaGetErrorString(e));
+    ctx->stream = user_stream;
+    ctx->frame_base = 0;
+    for (auto& ln : ctx->lanes) {
+        CK(ctx, cudaEventRecord(ln.done, ln.s));
+        CK(ctx, cudaStreamWaitEvent(user_stream, ln.done, 0));
+    }
+    if (rc) {
+        cudaStreamSynchronize(user_stream);
+        return rc;
+    }
+    u64 h[2] = {0, 0};
+    CK(ctx, cudaMemcpyAsync(h, ctx->d_counters, sizeof h, cudaMemcpyDeviceToHost, user_stream));
+    CK(ctx, cudaStreamSynchronize(user_stream));
     if (counters) {
         counters[0] += h[0];
         counters[1] += h[1];

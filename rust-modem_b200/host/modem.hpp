@@ -592,6 +592,14 @@ struct Loopback {
         check(modem_gpu_loopback(ctx.raw(), bits, F, nbits, sigma, seed, frame0, tx, sym, bits_out, cnt), ctx.raw(), "modem_gpu_loopback");
         return {cnt[0], cnt[1]};
     }
+    /* extension: packed payloads, 8 bits per byte, first bit = most significant (1/8 of the bytes over PCIe) */
+    std::pair<uint64_t, uint64_t> run_packed(const uint8_t* packed, size_t F, size_t nbits, uint8_t* packed_out, float sigma = 0.0f,
+                                             uint64_t seed = 0, uint64_t frame0 = 0)
+    {
+        uint64_t cnt[2] = {0, 0};
+        check(modem_gpu_loopback_packed(ctx.raw(), packed, F, nbits, sigma, seed, frame0, packed_out, cnt), ctx.raw(), "modem_gpu_loopback_packed");
+        return {cnt[0], cnt[1]};
+    }
 };
 } // namespace gpu
 

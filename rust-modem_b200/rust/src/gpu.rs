@@ -139,6 +139,8 @@ extern "C" {
     pub fn modem_gpu_loopback(ctx: *mut modem_ctx_t, bits: *const u8, f: usize, nbits: usize, sigma: f32, seed: u64,
                               frame0: u64, tx: *mut modem_c32_t, sym: *mut u8, bits_out: *mut u8,
                               counters: *mut u64) -> c_int;
+    pub fn modem_gpu_loopback_packed(ctx: *mut modem_ctx_t, packed: *const u8, f: usize, nbits: usize, sigma: f32,
+                                     seed: u64, frame0: u64, packed_out: *mut u8, counters: *mut u64) -> c_int;
     // ---- memory helpers
     pub fn modem_gpu_malloc(ctx: *mut modem_ctx_t, dptr: *mut *mut c_void, bytes: usize) -> c_int;
     pub fn modem_gpu_free(ctx: *mut modem_ctx_t, dptr: *mut c_void) -> c_int;
@@ -364,6 +366,22 @@ impl Context {
         check(unsafe { modem_gpu_loopback(self.raw, bits.as_ptr(), frames, nbits, sigma, seed, 0, std::ptr::null_mut(),
                                           std::ptr::null_mut(), bits_out.as_mut_ptr(), cnt.as_mut_ptr()) },
               self.raw, "modem_gpu_loopback");
+        (cnt[0], cnt[1])
+    }
+
+    /// Extension (not the reference's payload format): the loopback on PACKED payloads, 8 bits per byte with the first bit
+    /// in the most significant position (the order of `digital::util::bytes_to_bits`).  `packed` holds `frames` rows of
+    /// `ceil(nbits / 8)` bytes, `packed_out` receives `frames` rows of `ceil(K * bps / 8)` bytes.  Same decisions and
+    /// counters as `loopback` on the unpacked bits, 1/8 of the bytes over PCIe.
+    pub fn loopback_packed(&mut self, packed: &[u8], frames: usize, nbits: usize, packed_out: &mut [u8], sigma: f32, seed: u64) -> Counters {
+        assert!(packed.len() >= frames * ((nbits + 7) / 8));
+        let k = self.decided_symbols(self.frame_samples(nbits));
+        let ob = (k * self.bps + 7) / 8;
+        assert!(packed_out.len() >= frames * ob, "packed_out holds {} bytes, the call writes {}", packed_out.len(), frames * ob);
+        let mut cnt = [0u64; 2];
+        check(unsafe { modem_gpu_loopback_packed(self.raw, packed.as_ptr(), frames, nbits, sigma, seed, 0, packed_out.as_mut_ptr(),
+                                                 cnt.as_mut_ptr()) },
+              self.raw, "modem_gpu_loopback_packed");
         (cnt[0], cnt[1])
     }
 

@@ -23,7 +23,7 @@ def test_library_exports_every_declared_symbol(pkg):
     assert len(names) >= 42
     missing = [n for n in names if not hasattr(L, n)]
     assert not missing, missing
-    assert L.modem_gpu_abi_version() == 3
+    assert L.modem_gpu_abi_version() == 4
 
 
 def test_cfg_struct_matches_header(pkg):

@@ -782,3 +782,77 @@ def test_fused_loopback_bank_and_fallbacks(pkg, orc):
         assert_buffers(tx, o.modulate(b), f"fallback tx {over}")
         s_ref, b_ref, _ = o.loopback(b)
         assert np.array_equal(sym, s_ref) and np.array_equal(out, b_ref), over
+
+
+# ----------------------------------------------------------------------------- packed payloads (extension)
+@pytest.mark.parametrize("case", ["fused", "noisy", "shaped", "ragged", "bpsk_odd"])
+@pytest.mark.parametrize("chunk", [0, 3])
+def test_loopback_packed(pkg, orc, case, chunk, monkeypatch):
+    """modem_gpu_loopback_packed: packed rows in, packed rows out; decisions and counters are those of the oracle's
+    loopback on the unpacked bits (fused kernel, noisy two-kernel path with global frame ids across chunks, the 129-tap
+    pair, row lengths that are not multiples of 8 on either side)."""
+    if chunk:
+        monkeypatch.setenv("MODEM_GPU_PACKED_CHUNK", str(chunk))
+    scheme, nbits, F, sigma_db, kw = "qpsk", 2 * 704, 10, None, {}
+    if case == "noisy":
+        sigma_db = 4.0
+    elif case == "shaped":
+        kw = dict(shaped=True)
+    elif case == "ragged":
+        nbits = 2 * 701 + 1  # 1403 bits: the last packed byte carries 3 bits, the trailing half symbol is dropped
+    elif case == "bpsk_odd":
+        scheme, nbits = "bpsk", 517
+    pk = path_kwargs(scheme, sps=8, **kw)
+    m, o = make(pkg, orc, **pk)
+    bits = rand_bits(301, F, nbits)
+    sigma = o.sigma_for_ebn0(sigma_db) if sigma_db is not None else 0.0
+    _, bits_ref, cnt_ref = o.loopback(bits, sigma=sigma, seed=9, frame0=17, threads=4)
+    packed = orc.pack_bits(bits)
+    n0 = m.launch_count
+    got = m.loopback_packed(packed, nbits, sigma=sigma, seed=9, frame0=17)
+    assert np.array_equal(got["packed"], orc.pack_bits(bits_ref)), case
+    assert np.array_equal(orc.unpack_bits(got["packed"], bits_ref.shape[1]), bits_ref)
+    assert (got["errors"], got["compared"]) == cnt_ref
+    if case == "fused" and not chunk:
+        assert m.launch_count - n0 <= 4, "unpack + fused loopback kernel + pack (+ the NCO table)"
+    # pad bits of the input rows are ignored
+    if nbits % 8:
+        dirty = packed.copy()
+        dirty[:, -1] |= (1 << (8 - nbits % 8)) - 1
+        again = m.loopback_packed(dirty, nbits, sigma=sigma, seed=9, frame0=17)
+        assert np.array_equal(again["packed"], got["packed"])
+
+
+def test_loopback_packed_device_pointers_and_bank(pkg, orc):
+    """Device-resident packed rows run in place (no copies); a multi-carrier bank through the chunked host form."""
+    import torch
+
+    kw = path_kwargs("qpsk", sps=8)
+    m, o = make(pkg, orc, **kw)
+    F, nbits = 6, 2 * 640
+    bits = rand_bits(302, F, nbits)
+    _, bits_ref, cnt_ref = o.loopback(bits)
+    d_in = torch.from_numpy(orc.pack_bits(bits)).cuda()
+    K = m.decided_symbols(m.frame_samples(nbits))
+    d_out = torch.full((F, (2 * K + 7) // 8), 0xEE, dtype=torch.uint8, device="cuda")
+    cnt = m.loopback_packed_into(d_in, F, nbits, d_out)
+    assert np.array_equal(d_out.cpu().numpy(), orc.pack_bits(bits_ref))
+    assert cnt == cnt_ref
+    assert m.loopback_packed_into(d_in, F, nbits, None) == cnt_ref  # counters only
+    hz = [1100 + 333 * c for c in range(4)]
+    mb = pkg.Modem(**kw)
+    mb.set_channels([pkg.sample_freq(h, 10000) for h in hz], 3)
+    bits2 = rand_bits(303, 12, 2 * 600)
+    import os
+    os.environ["MODEM_GPU_PACKED_CHUNK"] = "5"  # not a divisor of the channel size: the chunk is cut to one
+    try:
+        mb2 = pkg.Modem(**kw)
+        mb2.set_channels([pkg.sample_freq(h, 10000) for h in hz], 3)
+        got = mb2.loopback_packed(orc.pack_bits(bits2), bits2.shape[1])
+    finally:
+        del os.environ["MODEM_GPU_PACKED_CHUNK"]
+    for c in range(4):
+        oc = orc.OraclePath(**dict(kw, carrier_hz=hz[c]))
+        _, b_ref, _ = oc.loopback(bits2[3 * c: 3 * c + 3])
+        assert np.array_equal(got["packed"][3 * c: 3 * c + 3], orc.pack_bits(b_ref)), f"channel {c}"
+    assert got["errors"] == 0

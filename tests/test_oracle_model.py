@@ -251,3 +251,22 @@ def test_random_bits_definition(orc):
             assert b[f, j] == (r[(j % 128) // 32] >> (j % 32)) & 1
     big = orc.random_bits(64, 16384, seed=1)
     assert abs(float(big.mean()) - 0.5) < 0.002 and set(np.unique(big)) == {0, 1}
+
+
+def test_packed_payload_definition(orc):
+    """Packed payload rows (extension): first bit = most significant bit of its byte (np.packbits order, the order of
+    bytes_to_bits, digital/util.rs:5-11), pad bits zero, unpack ignores them; only bit 0 of a bit byte counts."""
+    rng = np.random.default_rng(3)
+    for nbits in (1, 7, 8, 9, 64, 301):
+        bits = rng.integers(0, 2, (5, nbits), dtype=np.uint8)
+        packed = orc.pack_bits(bits)
+        assert packed.shape == (5, (nbits + 7) // 8)
+        assert np.array_equal(packed, np.packbits(bits, axis=1))
+        assert np.array_equal(orc.unpack_bits(packed, nbits), bits)
+        dirty = packed.copy()
+        if nbits % 8:
+            dirty[:, -1] |= (1 << (8 - nbits % 8)) - 1  # pad bits set: ignored
+        assert np.array_equal(orc.unpack_bits(dirty, nbits), bits)
+        assert np.array_equal(orc.pack_bits(bits | 0xFE), packed)
+    # bytes_to_bits of one whole byte is the byte: 0b10110001 -> bits 1,0,1,1,0,0,0,1
+    assert orc.unpack_bits(np.array([[0xB1]], np.uint8), 8).tolist() == [[1, 0, 1, 1, 0, 0, 0, 1]]
