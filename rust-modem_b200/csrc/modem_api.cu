@@ -458,9 +458,7 @@ int launch_rx(modem_ctx* ctx, const float2* d_rx, u64 F, u64 L, uint8_t* d_sym, 
     a.sample0 = c.sample0;
     a.taps = ctx->d_rx_taps;
     a.n_taps = c.n_rx_taps;
-    a.nz.sigma = sigma;
-    a.nz.seed = seed;
-    a.nz.frame0 = frame0;
+    a.nz = mg::make_noise(sigma, seed, frame0);
     if (src) {
         a.raw = src->raw;
         a.rx_fmt = src->fmt;
@@ -1182,7 +1180,7 @@ int modem_gpu_awgn(modem_ctx_t* ctx, modem_c32_t* buf, size_t F, size_t L, float
         d = (float2*)ctx->s_rx.p;
         CK(ctx, cudaMemcpyAsync(d, buf, bytes, cudaMemcpyHostToDevice, ctx->stream));
     }
-    mg::Noise nz{sigma, seed, frame0};
+    const mg::Noise nz = mg::make_noise(sigma, seed, frame0);
     const u64 quads = (u64)F * ((L + 3) / 4);
     const unsigned blocks = (unsigned)std::min<u64>((quads + mg::kThreads - 1) / mg::kThreads, (u64)ctx->sm_count * 32);
     mg::awgn_kernel<<<blocks, mg::kThreads, 0, ctx->stream>>>(d, F, L, nz);
