@@ -337,7 +337,7 @@ def other_configs(pkg, torch, dist, world, rank, local_rank, peak, which, steps=
 
     for w in which:
         if w == "c1":
-            rows.append(run_two_kernels("C1 rates", "the reference's default rates (sr 10000 / baud 220 -> sps 45, carrier 1000 Hz, modulate.rs:44-58), 4096 frames x 65520 samples, rect hold + 64-tap low-pass", 4096, 45, False))
+            rows.append(run_two_kernels("C1 rates", "the reference's default rates (sr 10000 / baud 220 -> sps 45, carrier 1000 Hz, modulate.rs:44-58), 4096 frames x 65520 samples, rect hold + 64-tap low-pass; fused_* = the same loopback as ONE kernel (rx_dec_kernel<..., TXF>)", 4096, 45, False, fused_ok=True))
         if w == "c3":
             rows.append(run_two_kernels("C3", "129-tap RRC both sides, sps 8, 16384 frames x 65536 = 2^30 samples per GPU, exact MACs", 16384, 8, True))
         if w == "c4":

@@ -570,16 +570,24 @@ bool loop_fused_eligible(modem_ctx* ctx, const uint8_t* d_bits, u64 F, u64 nbits
 {
     const modem_cfg_t& c = ctx->cfg;
     if (ctx->no_fused_loop || ctx->force_generic || ctx->phasor_on || sigma != 0.0f) return false;
-    if (c.n_tx_taps || c.bits_per_symbol != 2 || c.n_tables != 1 || c.q_offset || c.samples_per_symbol != 8 || c.n_rx_taps != 64 ||
+    if (c.n_tx_taps || c.bits_per_symbol != 2 || c.n_tables != 1 || c.q_offset || c.n_rx_taps != 64 ||
         (c.flags & MODEM_FLAG_FUSED_MAC) || !ctx->cs_rx_shared)
         return false;
-    if (!d_bits || (nbits & 7u) || (reinterpret_cast<uintptr_t>(d_bits) & 7u) || (d_tx && !aligned16(d_tx))) return false; /* 8-byte rows of bits */
-    a.L = (nbits / 2) * 8;
+    a.sps = c.samples_per_symbol;
+    a.L = (nbits / 2) * a.sps;
     a.F = F;
     a.K = modem_gpu_decided_symbols(ctx, a.L);
     if (F == 0 || a.L == 0 || a.K == 0 || a.L >= (1ull << 32)) return false;
     a.delay = c.decision_delay;
-    return mg::loop_fused_supported_64(a);
+    if (a.sps == 8) { /* the headline shape: rx_fast_kernel<..., TXF>, rows of bits read as 8-byte words */
+        if (!d_bits || (nbits & 7u) || (reinterpret_cast<uintptr_t>(d_bits) & 7u) || (d_tx && !aligned16(d_tx))) return false;
+        if (mg::loop_fused_supported_64(a)) return true;
+    }
+    /* any other samples-per-symbol count up to 64 (the reference's default rates: 45): rx_dec_kernel<..., TXF>, two bit bytes
+     * per symbol read as one 16-bit word */
+    if (ctx->no_rx_dec || !d_bits || (nbits & 1u) || (reinterpret_cast<uintptr_t>(d_bits) & 1u) || (d_tx && !aligned16(d_tx))) return false;
+    a.sym_tile = mg::rx_dec_tile_symbols(a.sps);
+    return a.sps != 8 && mg::loop_fused_dec_supported(a);
 }
 
 int launch_loop_fused(modem_ctx* ctx, const uint8_t* d_bits, u64 F, u64 nbits, float2* d_tx, uint8_t* d_sym, uint8_t* d_out,
@@ -588,6 +596,7 @@ int launch_loop_fused(modem_ctx* ctx, const uint8_t* d_bits, u64 F, u64 nbits, f
     const modem_cfg_t& c = ctx->cfg;
     mg::RxArgs a{};
     if (!d_counters || !loop_fused_eligible(ctx, d_bits, F, nbits, d_tx, sigma, a)) return 0;
+    const bool dec = a.sps != 8;
     a.sym = d_sym;
     a.bits = d_out;
     a.ref_bits = d_bits;
@@ -595,7 +604,6 @@ int launch_loop_fused(modem_ctx* ctx, const uint8_t* d_bits, u64 F, u64 nbits, f
     a.counters = d_counters;
     a.slut = ctx->d_slut;
     a.bps = 2;
-    a.sps = 8;
     a.n_tables = 1;
     a.n_const = 4;
     a.delay = c.decision_delay;
@@ -606,16 +614,22 @@ int launch_loop_fused(modem_ctx* ctx, const uint8_t* d_bits, u64 F, u64 nbits, f
     a.n_taps = 64;
     a.tx_out = d_tx;
     for (int j = 0; j < 4; ++j) a.tx_iq[j] = make_float2(ctx->h_const[2 * j], ctx->h_const[2 * j + 1]);
-    const u64 tiles = (a.K + mg::loop_fused_tile_symbols_64() - 1) / mg::loop_fused_tile_symbols_64();
-    a.frames_per_block = std::min<uint32_t>(frames_per_block(ctx, F, tiles), 16);
-    if (ctx->rx_fpb > 0 && !ctx->n_channels) a.frames_per_block = (uint32_t)std::max<u64>(ctx->rx_fpb, (F + 65534) / 65535);
-    if (ctx->n_channels) while (ctx->frames_per_channel % a.frames_per_block || ctx->frame_base % a.frames_per_block) --a.frames_per_block;
-    a.tile_major = ctx->rx_tile_major == 0 ? 0u : 1u;
+    if (dec) {
+        a.frames_per_block = frames_per_block(ctx, F, (a.K + a.sym_tile - 1) / a.sym_tile);
+    } else {
+        const u64 tiles = (a.K + mg::loop_fused_tile_symbols_64() - 1) / mg::loop_fused_tile_symbols_64();
+        a.frames_per_block = std::min<uint32_t>(frames_per_block(ctx, F, tiles), 16);
+        if (ctx->rx_fpb > 0 && !ctx->n_channels) a.frames_per_block = (uint32_t)std::max<u64>(ctx->rx_fpb, (F + 65534) / 65535);
+        if (ctx->n_channels) while (ctx->frames_per_channel % a.frames_per_block || ctx->frame_base % a.frames_per_block) --a.frames_per_block;
+        a.tile_major = ctx->rx_tile_major == 0 ? 0u : 1u;
+    }
     int rc = attach_carrier_table(ctx, a.ch, F, a.L, true);
     if (rc) return rc;
     if (!a.ch.cs_tab) return 0;
     set_sign_slicer(ctx, a);
-    cudaError_t e = mg::loop_fused_launch_64(a, ctx->h_rx_taps.data(), !(c.flags & MODEM_FLAG_NO_TMEM), ctx->stream);
+    const bool tmem = !(c.flags & MODEM_FLAG_NO_TMEM);
+    cudaError_t e = dec ? mg::loop_fused_dec_launch(a, ctx->h_rx_taps.data(), tmem, ctx->stream)
+                        : mg::loop_fused_launch_64(a, ctx->h_rx_taps.data(), tmem, ctx->stream);
     if (e != cudaSuccess) return fail(ctx, MODEM_ERR_CUDA, std::string("fused loopback: ") + cudaGetErrorString(e));
     ctx->launches++;
     return 1;

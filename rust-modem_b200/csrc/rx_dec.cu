@@ -30,7 +30,7 @@ constexpr int kDecThreads = 128; /* = symbols per tile */
 /* TMEM: the frame-invariant NCO values of a thread's first 32 chunks (128 values) are parked in tensor memory once per CTA
  * (128 columns x 4 CTAs = the SM's 512 columns, all 128 lanes used) and read back with tcgen05.ld every frame, instead of
  * 8 B/sample from the NCO table through L2/L1 next to the 8 B/sample of the signal itself. */
-template <int NT, bool FMA, bool TMEM>
+template <int NT, bool FMA, bool TMEM, bool TXF = false>
 __global__ void __launch_bounds__(kDecThreads, 4)
     rx_dec_kernel(const __grid_constant__ RxArgs a, const __grid_constant__ TapsParam<NT> taps)
 {
@@ -67,6 +67,48 @@ __global__ void __launch_bounds__(kDecThreads, 4)
         const long long n = nb0 + 2 * (long long)c;
         return c < NCH && n >= 0 && (u64)n < a.L; /* L is even: a pair is inside or outside */
     };
+    /* ---- TXF: the fused loopback for any samples-per-symbol count (the reference's default rates).  Phase A does not load
+     * the tile's TX samples, it MAKES them from the frame's bits (a.ref_bits, two bytes per symbol) with the arithmetic of
+     * the rectangular-hold TX kernel -- data.rs:66-79 hold, digital/qpsk.rs:23-35 as a 4-entry table (a.tx_iq),
+     * modulator.rs:37-48 mix, every operation rounded on its own --, stores them to a.tx_out once (a tile owns the samples
+     * from the end of the previous tile's staged range to the end of its own; the first tile owns the frame's head, the
+     * last one its tail: the launcher checks that the staged ranges leave no gap, sps <= NT) and stages their real parts
+     * like the unfused kernel.  The symbols a tile touches (at most 2 * kDecThreads: its own 128 plus (NT + 2) / sps + 2 of
+     * halo) reach the threads as (i, q) pairs through a small shared table, written when the previous frame's FIR is done
+     * from bit bytes fetched before it started.  Same NCO values on both sides (no phase offset: the launcher checks). */
+    __shared__ f32x2 s_sq[TXF ? 2 * kDecThreads : 1];
+    const long long first_n = nb0 < 0 ? 0 : nb0;                 /* first staged sample that exists */
+    const uint32_t ksym0 = TXF ? (uint32_t)((u64)first_n / sps) : 0u; /* table slot 0 */
+    const uint32_t magic = TXF ? 0xFFFFFFFFu / sps + 1u : 0u;    /* ceil(2^32 / sps): floor(x / sps) = umulhi(x, magic) for x < 2^32 / sps */
+    const long long loc0 = nb0 - (long long)ksym0 * sps;         /* sample nb0 relative to the first sample of symbol ksym0 (negative in the first tile) */
+    long long own_lo = 0, own_hi = 0;
+    if (TXF) {
+        if (k0 > 0) { /* the previous tile's staged range ends here */
+            const long long pnb = (long long)((k0 - TS) * sps + a.delay) - (long long)(NT - 1);
+            const long long pnb0 = pnb & ~1ll;
+            const uint32_t pR = (TS - 1) * sps + NT + (uint32_t)(pnb - pnb0);
+            own_lo = pnb0 + 2 * (long long)((pR + 1) / 2);
+        }
+        own_hi = (k0 + TS >= a.K) ? (long long)a.L : nb0 + 2 * (long long)NCH;
+    }
+    const u64 nsym = TXF ? a.ref_stride / 2 : 0; /* symbols per frame row (bps = 2) */
+    const bool store_tx = TXF && a.tx_out != nullptr;
+    uint32_t nw0 = 0, nw1 = 0; /* the next frame's bit bytes of this thread's two table slots */
+    auto fetch_syms = [&](u64 f) {
+        const uint8_t* row = a.ref_bits + f * a.ref_stride;
+        const u64 s0 = (u64)ksym0 + tid, s1 = s0 + kDecThreads;
+        nw0 = s0 < nsym ? (uint32_t)__ldg(reinterpret_cast<const unsigned short*>(row + 2 * s0)) : 0u;
+        nw1 = s1 < nsym ? (uint32_t)__ldg(reinterpret_cast<const unsigned short*>(row + 2 * s1)) : 0u;
+    };
+    auto park_syms = [&]() { /* symbol index = 2 b0 + b1, first byte = MSB (digital/util.rs:5-11); only bit 0 of a byte counts */
+        const float2 p0 = a.tx_iq[((nw0 & 1u) << 1) | ((nw0 >> 8) & 1u)], p1 = a.tx_iq[((nw1 & 1u) << 1) | ((nw1 >> 8) & 1u)];
+        s_sq[TXF ? tid : 0] = pk2(p0.x, p0.y);
+        s_sq[TXF ? tid + kDecThreads : 0] = pk2(p1.x, p1.y);
+    };
+    if (TXF && f0 < f1) {
+        fetch_syms(f0);
+        park_syms();
+    }
     if (TMEM) {
         taddr = tmem_alloc<128>(&s_tmem);
         twarp = tmem_warp_addr(taddr);
@@ -88,7 +130,7 @@ __global__ void __launch_bounds__(kDecThreads, 4)
         __syncthreads(); /* previous frame's FIR finished; s_slut visible */
         const float4* src = reinterpret_cast<const float4*>(a.rx + f * a.L + nb0);
         /* pull the NEXT frame's tile towards L2 while this one is staged and filtered: one bulk (TMA) prefetch per CTA */
-        if (tid == 0 && f + 1 < f1) {
+        if (!TXF && tid == 0 && f + 1 < f1) {
             const long long lo = nb0 < 0 ? 0 : nb0, hi = min((long long)a.L, nb0 + 2 * (long long)NCH);
             if (hi > lo) {
                 const char* nxt = reinterpret_cast<const char*>(a.rx + (f + 1) * a.L + lo);
@@ -98,23 +140,42 @@ __global__ void __launch_bounds__(kDecThreads, 4)
         auto stage = [&](uint32_t c, const float4& x, const float4& cs) { /* demodulator.rs:53-54, Q rail negated (see the header) */
             reinterpret_cast<ulonglong2*>(s_v)[c] = make_ulonglong2(mul2(pk2(x.x, x.x), pk2(cs.x, cs.y)), mul2(pk2(x.z, x.z), pk2(cs.z, cs.w)));
         };
+        float4* txrow = TXF ? reinterpret_cast<float4*>(a.tx_out + f * a.L + nb0) : nullptr;
+        /* TXF: the chunk's two TX samples from the symbol table and the NCO pair (cs = cos, sin of samples 2c, 2c + 1; zero
+         * outside the frame, where nothing is made or stored) */
+        auto make_tx = [&](uint32_t c, const float4& cs) -> float4 {
+            if (!chunk_ok(c)) return make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+            const uint32_t l0 = (uint32_t)(loc0 + 2 * (long long)c); /* >= 0 for a chunk inside the frame */
+            const float2 q0 = unpk2(s_sq[TXF ? __umulhi(l0, magic) : 0]), q1 = unpk2(s_sq[TXF ? __umulhi(l0 + 1u, magic) : 0]);
+            const f32x2 pm = pk2(-1.0f, 1.0f);
+            /* modulator.rs:37-43 on packed pairs: (i*c, i*s) and (q*s, q*c), then (i*c - q*s, i*s + q*c) by one fma with (-1, +1) */
+            const f32x2 x0 = fma2(mul2(pk2(q0.y, q0.y), pk2(cs.y, cs.x)), pm, mul2(pk2(q0.x, q0.x), pk2(cs.x, cs.y)));
+            const f32x2 x1 = fma2(mul2(pk2(q1.y, q1.y), pk2(cs.w, cs.z)), pm, mul2(pk2(q1.x, q1.x), pk2(cs.z, cs.w)));
+            const float4 x = make_float4(unpk2(x0).x, unpk2(x0).y, unpk2(x1).x, unpk2(x1).y);
+            const long long n = nb0 + 2 * (long long)c;
+            if (store_tx && n >= own_lo && n < own_hi) __stcs(txrow + c, x);
+            return x;
+        };
         uint32_t c0 = tid;
         if (TMEM) {
 #pragma unroll
             for (int b = 0; b < TRIPS_TM; ++b, c0 += U * kDecThreads) {
                 if (c0 - tid >= NCH) break; /* uniform: the tile has no more chunks */
                 float4 x[U];
+                if (!TXF) {
 #pragma unroll
-                for (int u = 0; u < U; ++u) {
-                    const uint32_t c = c0 + u * kDecThreads;
-                    x[u] = chunk_ok(c) ? __ldg(src + c) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                    for (int u = 0; u < U; ++u) {
+                        const uint32_t c = c0 + u * kDecThreads;
+                        x[u] = chunk_ok(c) ? __ldg(src + c) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                    }
                 }
                 float parked[32];
                 tmem_ld32(twarp + 32 * b, parked);
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
                     const uint32_t c = c0 + u * kDecThreads;
-                    if (c < NCH) stage(c, x[u], make_float4(parked[4 * u], parked[4 * u + 1], parked[4 * u + 2], parked[4 * u + 3]));
+                    const float4 cs = make_float4(parked[4 * u], parked[4 * u + 1], parked[4 * u + 2], parked[4 * u + 3]);
+                    if (c < NCH) stage(c, TXF ? make_tx(c, cs) : x[u], cs);
                 }
             }
         }
@@ -124,16 +185,17 @@ __global__ void __launch_bounds__(kDecThreads, 4)
             for (int u = 0; u < U; ++u) {
                 const uint32_t c = c0 + u * kDecThreads;
                 const bool ok = chunk_ok(c);
-                x[u] = ok ? __ldg(src + c) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                x[u] = (ok && !TXF) ? __ldg(src + c) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
                 cs[u] = ok ? __ldg(cs4 + c) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
             }
 #pragma unroll
             for (int u = 0; u < U; ++u) {
                 const uint32_t c = c0 + u * kDecThreads;
-                if (c < NCH) stage(c, x[u], cs[u]);
+                if (c < NCH) stage(c, TXF ? make_tx(c, cs[u]) : x[u], cs[u]);
             }
         }
         __syncthreads();
+        if (TXF && f + 1 < f1) fetch_syms(f + 1); /* the next frame's bit bytes fly during the FIR */
         if (live) {
             /* fir.rs:21-24 on both rails at once: acc = fl(acc + fl(v * h)), taps 0..NT-1 in order */
             f32x2 acc = 0ull, pend = 0ull;
@@ -160,6 +222,7 @@ __global__ void __launch_bounds__(kDecThreads, 4)
             err += emit_symbol(a, f, k, s, I, Q);
             cmp += a.ref_bits ? a.bps : 0u;
         }
+        if (TXF && f + 1 < f1) park_syms(); /* read again only behind the barrier at the top of the next frame */
     }
     block_count(a, err, cmp);
     if (TMEM) tmem_free<128>(taddr);
@@ -171,11 +234,11 @@ uint32_t rx_dec_tile_symbols(uint32_t sps)
     (void)sps;
     return kDecThreads; /* (127 sps + 66) * 8 B of shared memory: 46 KB at sps 45, 183 KB at sps 180 */
 }
-template <int NT, bool FMA, bool TMEM>
+template <int NT, bool FMA, bool TMEM, bool TXF = false>
 static cudaError_t rx_dec_launch_t(const RxArgs& a, const float* h_taps, cudaStream_t stream)
 {
     const size_t smem = ((size_t)(a.sym_tile - 1) * a.sps + NT + 2) * sizeof(f32x2);
-    auto kern = rx_dec_kernel<NT, FMA, TMEM>;
+    auto kern = rx_dec_kernel<NT, FMA, TMEM, TXF>;
     static std::atomic<size_t> configured[kMaxDevices]; /* per device: the attribute is per device */
     int dev = 0;
     cudaError_t e = cudaGetDevice(&dev);
@@ -195,6 +258,26 @@ cudaError_t rx_dec_launch(const RxArgs& a, const float* h_taps, bool fma, bool t
 {
     if (tmem) return fma ? rx_dec_launch_t<64, true, true>(a, h_taps, stream) : rx_dec_launch_t<64, false, true>(a, h_taps, stream);
     return fma ? rx_dec_launch_t<64, true, false>(a, h_taps, stream) : rx_dec_launch_t<64, false, false>(a, h_taps, stream);
+}
+
+/* ---- the fused loopback at any samples-per-symbol count (rx_dec_kernel<..., TXF>): geometry test and launcher.
+ * a.L, a.K, a.sps, a.delay and a.sym_tile must be set.  The tiles' staged ranges must cover [0, L) without a gap: the
+ * first tile starts at or before sample 0 (delay <= NT - 1), consecutive tiles overlap (sps <= NT) and the last one
+ * reaches the frame's end. */
+bool loop_fused_dec_supported(const RxArgs& a)
+{
+    constexpr uint32_t NT = 64;
+    const uint32_t sps = a.sps, TS = kDecThreads;
+    if (!rx_dec_supported(NT, sps) || sps > NT || a.delay > NT - 1 || a.K == 0 || (a.L & 1) || a.L >= (1ull << 32) / sps) return false;
+    const u64 tiles = (a.K + TS - 1) / TS;
+    const long long nb = (long long)((tiles - 1) * TS * sps + a.delay) - (long long)(NT - 1), nb0 = nb & ~1ll;
+    const long long R = (long long)(TS - 1) * sps + NT + (nb - nb0);
+    return nb0 + 2 * ((R + 1) / 2) >= (long long)a.L;
+}
+cudaError_t loop_fused_dec_launch(const RxArgs& a, const float* h_taps, bool tmem, cudaStream_t stream)
+{
+    if (tmem) return rx_dec_launch_t<64, false, true, true>(a, h_taps, stream);
+    return rx_dec_launch_t<64, false, false, true>(a, h_taps, stream);
 }
 
 } /* namespace mg */

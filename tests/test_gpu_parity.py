@@ -784,6 +784,68 @@ def test_fused_loopback_bank_and_fallbacks(pkg, orc):
         assert np.array_equal(sym, s_ref) and np.array_equal(out, b_ref), over
 
 
+def _dec_fused_shape(L, K, sps, delay):
+    """loop_fused_dec_supported (rx_dec.cu) restated: the tiles' staged ranges cover [0, L) without a gap."""
+    NT, TS = 64, 128
+    if sps == 8 or sps > NT or delay > NT - 1 or K == 0 or L % 2:
+        return False
+    tiles = (K + TS - 1) // TS
+    nb = (tiles - 1) * TS * sps + delay - (NT - 1)
+    nb0 = nb & ~1
+    R = (TS - 1) * sps + NT + (nb - nb0)
+    return nb0 + 2 * ((R + 1) // 2) >= L
+
+
+@pytest.mark.parametrize("sps,F,nsym", [(45, 5, 300), (45, 17, 1456), (45, 3, 128), (45, 2, 129), (45, 1, 4), (45, 4, 257), (10, 6, 777), (5, 9, 1500),
+                                        (4, 4, 1001), (3, 7, 2000), (3, 5, 2 * 128 + 22), (45, 3, 255), (10, 33, 128 * 3)])
+def test_fused_loopback_any_sps(pkg, orc, sps, F, nsym, monkeypatch):
+    """The fused loopback at the reference's default rates and other samples-per-symbol counts (rx_dec_kernel<..., TXF>):
+    TX buffer bit-identical to the oracle and completely written (NaN pre-fill), symbols, bits and counters equal, one
+    kernel when the tiles cover the frame; shapes that do not qualify (odd frame lengths, tiles that stop short of the
+    frame's end) run the two kernels with the same results.  MODEM_FLAG_NO_TMEM and a missing TX buffer change nothing."""
+    kw = path_kwargs("qpsk", sps=sps)
+    bits = rand_bits(400 + sps + F, F, 2 * nsym)
+    m, o = make(pkg, orc, **kw)
+    tx_ref = o.modulate(bits)
+    sym_ref, bits_ref, cnt_ref = o.loopback(bits, threads=4)
+    tx, sym, out, cnt, launches = _device_loopback(pkg, m, bits)
+    assert_buffers(tx, tx_ref, f"fused tx sps {sps}")
+    assert np.array_equal(sym, sym_ref) and np.array_equal(out, bits_ref)
+    assert cnt == (cnt_ref[0], cnt_ref[1])
+    L = m.frame_samples(2 * nsym)
+    fused = _dec_fused_shape(L, m.decided_symbols(L), sps, kw["decision_delay"])
+    assert launches == (2 if fused else 3), (launches, fused)  # NCO table + kernel(s)
+    if fused:
+        m3 = pkg.Modem(flags=pkg.FLAG_NO_TMEM, **kw)
+        tx3, sym3, out3, cnt3, l3 = _device_loopback(pkg, m3, bits)
+        assert l3 == 2 and np.array_equal(tx3.view(np.uint32), tx_ref.view(np.uint32)) and np.array_equal(out3, bits_ref) and cnt3 == cnt
+        tx4, sym4, out4, cnt4, l4 = _device_loopback(pkg, m, bits, want_tx=False)
+        assert tx4 is None and l4 == 1 and np.array_equal(sym4, sym_ref) and cnt4 == cnt
+    monkeypatch.setenv("MODEM_GPU_NO_FUSED_LOOP", "1")
+    m2 = pkg.Modem(**kw)
+    tx2, sym2, out2, cnt2, launches2 = _device_loopback(pkg, m2, bits)
+    assert launches2 == 3 and np.array_equal(tx.view(np.uint32), tx2.view(np.uint32))
+    assert np.array_equal(sym, sym2) and np.array_equal(out, out2) and cnt == cnt2
+
+
+def test_fused_loopback_any_sps_bank(pkg, orc):
+    """A carrier bank at the reference's default rates through the fused kernel: one NCO table row per channel."""
+    kw = path_kwargs("qpsk", sps=45)
+    hz = [700 + 411 * c for c in range(5)]
+    mb = pkg.Modem(**kw)
+    mb.set_channels([pkg.sample_freq(h, 10000) for h in hz], 4)
+    bits = rand_bits(81, 20, 2 * 300)
+    tx, sym, out, cnt, launches = _device_loopback(pkg, mb, bits)
+    assert launches == 2
+    for c in range(5):
+        oc = orc.OraclePath(**dict(kw, carrier_hz=hz[c]))
+        rows = slice(4 * c, 4 * c + 4)
+        assert_buffers(tx[rows], oc.modulate(bits[rows]), f"bank tx, channel {c}")
+        s_ref, b_ref, _ = oc.loopback(bits[rows])
+        assert np.array_equal(sym[rows], s_ref) and np.array_equal(out[rows], b_ref)
+    assert cnt[1] == out.size
+
+
 # ----------------------------------------------------------------------------- packed payloads (extension)
 @pytest.mark.parametrize("case", ["fused", "noisy", "shaped", "ragged", "bpsk_odd"])
 @pytest.mark.parametrize("chunk", [0, 3])
