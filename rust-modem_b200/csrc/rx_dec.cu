@@ -58,15 +58,20 @@ __global__ void __launch_bounds__(kDecThreads, 4)
     const f32x2* mine = s_v + (size_t)tid * sps + (NT - 1) + shift; /* the decision instant of this thread's symbol */
     const bool lut4 = a.n_const == 4 && a.n_tables == 1;
     const uint32_t toff = (uint32_t)(k % a.n_tables) * a.n_const;
+    const bool pair_io = a.bps == 2 && (reinterpret_cast<uintptr_t>(a.bits) & 1u) == 0 && (reinterpret_cast<uintptr_t>(a.ref_bits) & 1u) == 0 &&
+                         (a.ref_stride & 1u) == 0;
 
     constexpr int U = 8;        /* chunks per thread and trip: all loads of a trip are in flight before the first use */
     constexpr int TRIPS_TM = 4; /* trips whose NCO values live in tensor memory: 4 x 8 chunks x 4 values = 128 columns */
     __shared__ uint32_t s_tmem;
     uint32_t taddr = 0, twarp = 0;
-    auto chunk_ok = [&](uint32_t c) {
-        const long long n = nb0 + 2 * (long long)c;
-        return c < NCH && n >= 0 && (u64)n < a.L; /* L is even: a pair is inside or outside */
-    };
+    /* the staged chunks that exist in the frame, as a range of chunk indices [vlo, vlo + vspan): L and nb0 are even, so a
+     * 16-byte pair is inside the frame or outside; one unsigned compare per chunk */
+    const uint32_t vlo = nb0 < 0 ? (uint32_t)((-nb0) >> 1) : 0u;
+    const long long vend = ((long long)a.L - nb0) >> 1; /* first chunk behind the frame's end (> 0: the tile has a live symbol) */
+    const uint32_t vhi = vend < (long long)NCH ? (uint32_t)(vend < 0 ? 0 : vend) : NCH;
+    const uint32_t vspan = vhi > vlo ? vhi - vlo : 0u;
+    auto chunk_ok = [&](uint32_t c) { return c - vlo < vspan; };
     /* ---- TXF: the fused loopback for any samples-per-symbol count (the reference's default rates).  Phase A does not load
      * the tile's TX samples, it MAKES them from the frame's bits (a.ref_bits, two bytes per symbol) with the arithmetic of
      * the rectangular-hold TX kernel -- data.rs:66-79 hold, digital/qpsk.rs:23-35 as a 4-entry table (a.tx_iq),
@@ -81,16 +86,20 @@ __global__ void __launch_bounds__(kDecThreads, 4)
     const uint32_t ksym0 = TXF ? (uint32_t)((u64)first_n / sps) : 0u; /* table slot 0 */
     const uint32_t magic = TXF ? 0xFFFFFFFFu / sps + 1u : 0u;    /* ceil(2^32 / sps): floor(x / sps) = umulhi(x, magic) for x < 2^32 / sps */
     const long long loc0 = nb0 - (long long)ksym0 * sps;         /* sample nb0 relative to the first sample of symbol ksym0 (negative in the first tile) */
-    long long own_lo = 0, own_hi = 0;
+    uint32_t olo = 0, ospan = 0; /* the chunks whose TX samples this tile stores: [olo, olo + ospan), inside [vlo, vhi) */
     if (TXF) {
+        long long own_lo = 0;
         if (k0 > 0) { /* the previous tile's staged range ends here */
             const long long pnb = (long long)((k0 - TS) * sps + a.delay) - (long long)(NT - 1);
             const long long pnb0 = pnb & ~1ll;
             const uint32_t pR = (TS - 1) * sps + NT + (uint32_t)(pnb - pnb0);
             own_lo = pnb0 + 2 * (long long)((pR + 1) / 2);
         }
-        own_hi = (k0 + TS >= a.K) ? (long long)a.L : nb0 + 2 * (long long)NCH;
+        const long long lo_c = (own_lo - nb0) >> 1; /* own_lo is even and >= max(nb0, 0) */
+        olo = lo_c < (long long)vlo ? vlo : (uint32_t)lo_c;
+        ospan = vhi > olo ? vhi - olo : 0u; /* a tile stores up to the end of its staged range; the last one reaches the frame's end */
     }
+    const uint32_t loc0u = (uint32_t)loc0; /* modulo 2^32: only sums that are >= 0 are used */
     const u64 nsym = TXF ? a.ref_stride / 2 : 0; /* symbols per frame row (bps = 2) */
     const bool store_tx = TXF && a.tx_out != nullptr;
     uint32_t nw0 = 0, nw1 = 0; /* the next frame's bit bytes of this thread's two table slots */
@@ -145,15 +154,14 @@ __global__ void __launch_bounds__(kDecThreads, 4)
          * outside the frame, where nothing is made or stored) */
         auto make_tx = [&](uint32_t c, const float4& cs) -> float4 {
             if (!chunk_ok(c)) return make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-            const uint32_t l0 = (uint32_t)(loc0 + 2 * (long long)c); /* >= 0 for a chunk inside the frame */
+            const uint32_t l0 = loc0u + 2u * c; /* >= 0 for a chunk inside the frame */
             const float2 q0 = unpk2(s_sq[TXF ? __umulhi(l0, magic) : 0]), q1 = unpk2(s_sq[TXF ? __umulhi(l0 + 1u, magic) : 0]);
             const f32x2 pm = pk2(-1.0f, 1.0f);
             /* modulator.rs:37-43 on packed pairs: (i*c, i*s) and (q*s, q*c), then (i*c - q*s, i*s + q*c) by one fma with (-1, +1) */
             const f32x2 x0 = fma2(mul2(pk2(q0.y, q0.y), pk2(cs.y, cs.x)), pm, mul2(pk2(q0.x, q0.x), pk2(cs.x, cs.y)));
             const f32x2 x1 = fma2(mul2(pk2(q1.y, q1.y), pk2(cs.w, cs.z)), pm, mul2(pk2(q1.x, q1.x), pk2(cs.z, cs.w)));
             const float4 x = make_float4(unpk2(x0).x, unpk2(x0).y, unpk2(x1).x, unpk2(x1).y);
-            const long long n = nb0 + 2 * (long long)c;
-            if (store_tx && n >= own_lo && n < own_hi) __stcs(txrow + c, x);
+            if (store_tx && c - olo < ospan) __stcs(txrow + c, x);
             return x;
         };
         uint32_t c0 = tid;
@@ -219,7 +227,17 @@ __global__ void __launch_bounds__(kDecThreads, 4)
                 s = ((~__float_as_uint(I) >> 31) << 1) | (~__float_as_uint(Q) >> 31);
             else
                 s = lut4 ? slice_point(s_slut, 4, I, Q) : slice_point(s_slut + toff, a.n_const, I, Q);
-            err += emit_symbol(a, f, k, s, I, Q);
+            if (pair_io) { /* bps = 2: the two bit bytes of a symbol as one 16-bit word, first byte = MSB (digital/util.rs:5-11) */
+                const u64 o = f * a.K + k;
+                const uint32_t bw = (s >> 1) | ((s & 1u) << 8);
+                if (a.sym) a.sym[o] = (uint8_t)s;
+                if (a.soft) a.soft[o] = make_float2(I, Q);
+                if (a.bits) *reinterpret_cast<unsigned short*>(a.bits + 2 * o) = (unsigned short)bw;
+                if (a.ref_bits) /* only bit 0 of a reference byte counts, as in pack_symbol */
+                    err += __popc((bw ^ (uint32_t)__ldg(reinterpret_cast<const unsigned short*>(a.ref_bits + f * a.ref_stride + 2 * k))) & 0x0101u);
+            } else {
+                err += emit_symbol(a, f, k, s, I, Q);
+            }
             cmp += a.ref_bits ? a.bps : 0u;
         }
         if (TXF && f + 1 < f1) park_syms(); /* read again only behind the barrier at the top of the next frame */

@@ -73,6 +73,9 @@ CASES = [
     ("generic kernels, odd frame length", "qpsk", 3, False, 6, 333, None, {}),
     ("oqpsk half-symbol offset", "oqpsk", 8, False, 4, 160, None, {}),
     ("no tensor memory", "qpsk", 8, False, 10, 700, None, {"flags": "NO_TMEM"}),
+    ("fused loopback at the reference's default rates (sps 45)", "qpsk", 45, False, 5, 300, None, {}),
+    ("fused loopback, sps 5, three tiles, no tensor memory", "qpsk", 5, False, 7, 300, None, {"flags": "NO_TMEM"}),
+    ("fused loopback, sps 3, frame shorter than a tile", "qpsk", 3, False, 3, 90, None, {}),
 ]
 
 

@@ -18,7 +18,7 @@ SPS, BPS, NSYM = 8, 2, 8192
 NBITS, L = NSYM * BPS, NSYM * SPS
 
 
-def run(name, F, shaped, flags=0, sigma_db=None, channels=0, steps=5, sps=8):
+def run(name, F, shaped, flags=0, sigma_db=None, channels=0, steps=5, sps=8, loop=False):
     global SPS, NSYM, NBITS, L
     SPS = sps
     NSYM = 65536 // sps
@@ -44,6 +44,23 @@ def run(name, F, shaped, flags=0, sigma_db=None, channels=0, steps=5, sps=8):
     cnt = torch.zeros(2, dtype=torch.int64, device="cuda")
     sigma = m.sigma_for_ebn0(sigma_db) if sigma_db is not None else 0.0
     ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(steps)]
+    if loop:  # the loopback entry: ONE fused kernel where the shape allows
+        for i in range(3 + steps):
+            cnt.zero_()
+            e = ev[i - 3] if i >= 3 else None
+            if e: e[0].record(st)
+            m.loopback_device_into(bits, F, NBITS, cnt, tx=tx, sym=sym, bits_out=out)
+            if e: e[1].record(st)
+        torch.cuda.synchronize()
+        ms = float(np.mean([e[0].elapsed_time(e[1]) for e in ev]))
+        b = 8 + BPS / SPS + (1 + BPS) / SPS
+        print(json.dumps({"config": name, "frames": F, "loop_ms": round(ms, 4), "loopback_Msamples_s": round(F * L / ms / 1e3, 0),
+                          "GBs": round(F * L * b / ms / 1e6, 0), "frac": round(F * L * b / ms / 1e6 / PEAK, 3), "bytes_per_sample": b,
+                          "errors": int(cnt[0]), "bits": int(cnt[1])}), flush=True)
+        m.close()
+        del tx
+        torch.cuda.empty_cache()
+        return
     for i in range(3 + steps):
         cnt.zero_()
         e = ev[i - 3] if i >= 3 else None
@@ -72,6 +89,8 @@ if __name__ == "__main__":
     FUSED = pkg.FLAG_FUSED_MAC
     for w in which:
         if w == "c1": run("C1 rates (sr 10000 / baud 220 -> sps 45, 1000 Hz), 4096 frames x 65520 samples (tx_rect_fast + rx_dec kernels)", 4096, False, sps=45)
+        if w == "c1l": run("C1 rates, the loopback entry (ONE fused kernel: rx_dec_kernel<..., TXF>)", 4096, False, sps=45, loop=True)
+        if w == "c2l": run("C2, the loopback entry (ONE fused kernel: rx_fast_kernel<..., TXF>)", 4096, False, loop=True)
         if w == "c2": run("C2 rect+lp64 exact", 4096, False)
         if w == "c2f": run("C2 rect+lp64 fused-MAC", 4096, False, flags=FUSED)
         if w == "c3": run("C3 rrc129 exact (16384 frames = 2^30 samples)", 16384, True, steps=3)
