@@ -153,9 +153,11 @@ __global__ void __launch_bounds__(kDecThreads, 4)
         /* TXF: the chunk's two TX samples from the symbol table and the NCO pair (cs = cos, sin of samples 2c, 2c + 1; zero
          * outside the frame, where nothing is made or stored) */
         auto make_tx = [&](uint32_t c, const float4& cs) -> float4 {
-            if (!chunk_ok(c)) return make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+            /* no branch for chunks outside the frame: their NCO pairs are zero (the staged values become +-0, which no FIR sum
+             * notices), their table slot is clamped into the table (every slot holds a finite pair) and they are never stored */
             const uint32_t l0 = loc0u + 2u * c; /* >= 0 for a chunk inside the frame */
-            const float2 q0 = unpk2(s_sq[TXF ? __umulhi(l0, magic) : 0]), q1 = unpk2(s_sq[TXF ? __umulhi(l0 + 1u, magic) : 0]);
+            constexpr uint32_t SMAX = 2 * kDecThreads - 1;
+            const float2 q0 = unpk2(s_sq[TXF ? min(__umulhi(l0, magic), SMAX) : 0]), q1 = unpk2(s_sq[TXF ? min(__umulhi(l0 + 1u, magic), SMAX) : 0]);
             const f32x2 pm = pk2(-1.0f, 1.0f);
             /* modulator.rs:37-43 on packed pairs: (i*c, i*s) and (q*s, q*c), then (i*c - q*s, i*s + q*c) by one fma with (-1, +1) */
             const f32x2 x0 = fma2(mul2(pk2(q0.y, q0.y), pk2(cs.y, cs.x)), pm, mul2(pk2(q0.x, q0.x), pk2(cs.x, cs.y)));
@@ -169,22 +171,28 @@ __global__ void __launch_bounds__(kDecThreads, 4)
 #pragma unroll
             for (int b = 0; b < TRIPS_TM; ++b, c0 += U * kDecThreads) {
                 if (c0 - tid >= NCH) break; /* uniform: the tile has no more chunks */
-                float4 x[U];
-                if (!TXF) {
+                /* FULL: every chunk of the trip is a staged chunk (uniform), no per-chunk range test */
+                auto trip = [&](auto full_c) {
+                    constexpr bool FULL = decltype(full_c)::value;
+                    float4 x[U];
+                    if (!TXF) {
+#pragma unroll
+                        for (int u = 0; u < U; ++u) {
+                            const uint32_t c = c0 + u * kDecThreads;
+                            x[u] = chunk_ok(c) ? __ldg(src + c) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                        }
+                    }
+                    float parked[32];
+                    tmem_ld32(twarp + 32 * b, parked);
 #pragma unroll
                     for (int u = 0; u < U; ++u) {
                         const uint32_t c = c0 + u * kDecThreads;
-                        x[u] = chunk_ok(c) ? __ldg(src + c) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                        const float4 cs = make_float4(parked[4 * u], parked[4 * u + 1], parked[4 * u + 2], parked[4 * u + 3]);
+                        if (FULL || c < NCH) stage(c, TXF ? make_tx(c, cs) : x[u], cs);
                     }
-                }
-                float parked[32];
-                tmem_ld32(twarp + 32 * b, parked);
-#pragma unroll
-                for (int u = 0; u < U; ++u) {
-                    const uint32_t c = c0 + u * kDecThreads;
-                    const float4 cs = make_float4(parked[4 * u], parked[4 * u + 1], parked[4 * u + 2], parked[4 * u + 3]);
-                    if (c < NCH) stage(c, TXF ? make_tx(c, cs) : x[u], cs);
-                }
+                };
+                if (c0 - tid + U * kDecThreads <= NCH) trip(std::true_type{});
+                else trip(std::false_type{});
             }
         }
         for (; c0 < NCH; c0 += U * kDecThreads) { /* chunks beyond the parked ones (large sps), or all of them without TMEM */
