@@ -32,13 +32,13 @@ __global__ void k(float* out, const float* in, int iters, const __grid_constant_
             for (int i = 0; i < N; ++i) {
                 if (MODE == 0) { float2 a = *reinterpret_cast<float2*>(&acc[i]); a.x = ffma(a.x, r0, r1); a.y = ffma(a.y, r1, r0); acc[i] = pk(a.x, a.y); }
                 if (MODE == 1) { float2 a = *reinterpret_cast<float2*>(&acc[i]); a.x = ffma(a.x, p.h[t], r1); a.y = ffma(a.y, p.h[t], r0); acc[i] = pk(a.x, a.y); }
-                if (MODE == 2) acc[i] = fma2(acc[i], one, mul2(v[i], hh));
+                if (MODE == 2) acc[i] = fma2(acc[i], one, mul2(acc[(i + 1) % N], hh)); /* the multiplicand changes every step: nothing can be hoisted out of the loop */
                 if (MODE == 3) acc[i] = fma2(acc[i], hh, v[i]);
                 if (MODE == 4) acc[i] = mul2(acc[i], hh);
                 if (MODE == 5) acc[i] = fma2(acc[i], v[i], v[(i + 1) % N]);
-                if (MODE == 6) { float2 a = *reinterpret_cast<float2*>(&acc[i]); float2 w = *reinterpret_cast<float2*>(&v[i]); a.x = fadd(a.x, fmul(w.x, p.h[t])); a.y = fadd(a.y, fmul(w.y, p.h[t])); acc[i] = pk(a.x, a.y); }
-                if (MODE == 7) { float2 a = *reinterpret_cast<float2*>(&acc[i]); u64 pr = mul2(v[i], hh); float2 w = *reinterpret_cast<float2*>(&pr); a.x = fadd(a.x, w.x); a.y = fadd(a.y, w.y); acc[i] = pk(a.x, a.y); }
-                if (MODE == 8) { float2 w = *reinterpret_cast<float2*>(&v[i]); acc[i] = fma2(acc[i], one, pk(fmul(w.x, p.h[t]), fmul(w.y, p.h[t]))); }
+                if (MODE == 6) { float2 a = *reinterpret_cast<float2*>(&acc[i]); float2 w = *reinterpret_cast<float2*>(&acc[(i + 1) % N]); a.x = fadd(a.x, fmul(w.x, p.h[t])); a.y = fadd(a.y, fmul(w.y, p.h[t])); acc[i] = pk(a.x, a.y); }
+                if (MODE == 7) { float2 a = *reinterpret_cast<float2*>(&acc[i]); u64 pr = mul2(acc[(i + 1) % N], hh); float2 w = *reinterpret_cast<float2*>(&pr); a.x = fadd(a.x, w.x); a.y = fadd(a.y, w.y); acc[i] = pk(a.x, a.y); }
+                if (MODE == 8) { float2 w = *reinterpret_cast<float2*>(&acc[(i + 1) % N]); acc[i] = fma2(acc[i], one, pk(fmul(w.x, p.h[t]), fmul(w.y, p.h[t]))); }
             }
         }
     }
