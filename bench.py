@@ -38,7 +38,7 @@ PATH = dict(scheme="qpsk", baud_rate=1250, sample_rate=10000, carrier_hz=2500)
 WORKLOAD = "C2: 4096 frames x 65536 complex f32 samples per GPU, QPSK, sps 8, rect hold + 64-tap low-pass, no noise"
 # sources whose change invalidates the committed dram__bytes capture (profiles/traffic.json)
 TRAFFIC_SOURCES = ["rust-modem_b200/csrc/rx_fast.cuh", "rust-modem_b200/csrc/common.cuh", "rust-modem_b200/csrc/loop_fused_64.cu",
-                   "rust-modem_b200/csrc/tx_fast.cu", "rust-modem_b200/csrc/rx_fast_64.cu"]
+                   "rust-modem_b200/csrc/tx_fast.cu", "rust-modem_b200/csrc/rx_fast_64.cu", "rust-modem_b200/csrc/rx_dec.cu"]
 
 
 def path_kwargs(lowpass):

@@ -269,8 +269,10 @@ int modem_gpu_ber_sweep(modem_ctx_t* ctx, const uint8_t* bits, size_t F, size_t 
  * accumulated into.  The headline shape (QPSK table, rectangular hold, 8 samples per symbol, the 64-tap low-pass
  * of src/bin/demodulate.rs:82-147, odd decision delay, exact MACs, sigma == 0, no phase offset, rows of bits on
  * 8-byte boundaries) runs as ONE fused kernel that makes the TX samples, stores them to tx (not at all when tx is
- * null) and demodulates them from registers; every buffer is bit-identical to the two-kernel path, which all other
- * shapes take (tx null => context scratch).  MODEM_GPU_NO_FUSED_LOOP=1 forces two kernels; MODEM_GPU_LOOP_CHUNK=n
+ * null) and demodulates them from registers; every buffer is bit-identical to the two-kernel path.  The same holds for
+ * any other samples-per-symbol count up to 64 with that table / filter (the reference's default rates, sps 45:
+ * rates.rs:16 with modulate.rs:44-58; decision delay <= 63, even frame length, rows of bits on 2-byte boundaries).  All
+ * other shapes take the two kernels (tx null => context scratch).  MODEM_GPU_NO_FUSED_LOOP=1 forces two kernels; MODEM_GPU_LOOP_CHUNK=n
  * cuts the two-kernel path into chunks of n frames with TX(c+1) || RX(c) on two streams (measured slower). */
 int modem_gpu_loopback_device(modem_ctx_t* ctx, const uint8_t* bits, size_t F, size_t nbits,
                               float sigma, uint64_t seed, uint64_t frame0, modem_c32_t* tx,

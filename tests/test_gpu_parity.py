@@ -568,6 +568,52 @@ def test_full_size_c3_properties(pkg, orc):
     assert np.array_equal(d_sym[idx].cpu().numpy(), sym_ref)
 
 
+def test_full_size_c1_rates_fused_and_two_kernels(pkg, orc):
+    """The reference's default rates (sr 10000 / baud 220 -> sps 45, carrier 1000 Hz, 64-tap low-pass) at the bench's size:
+    4096 frames x 65520 samples (12 tiles per frame).  ONE fused kernel (rx_dec_kernel<..., TXF>) and TX + RX: round trip
+    without a bit error, TX buffers of both forms identical in every bit (NaN pre-fill: completely written), symbols and
+    bits identical, sampled frames against the oracle."""
+    import torch
+
+    F, nsym = 4096, 1456
+    kw = path_kwargs("qpsk", sps=45)
+    o = orc.OraclePath(**kw)
+    g = torch.Generator(device="cuda").manual_seed(145)
+    d_bits = torch.randint(0, 2, (F, 2 * nsym), dtype=torch.uint8, device="cuda", generator=g)
+    res = {}
+    for form in ("fused", "two kernels"):
+        m = pkg.Modem(**kw)
+        m.set_stream(torch.cuda.current_stream().cuda_stream)
+        L = m.frame_samples(2 * nsym)
+        K = m.decided_symbols(L)
+        assert (L, K) == (65520, 1455)
+        d_tx = torch.full((F, L, 2), float("nan"), dtype=torch.float32, device="cuda")
+        d_sym = torch.empty((F, K), dtype=torch.uint8, device="cuda")
+        d_out = torch.empty((F, K * 2), dtype=torch.uint8, device="cuda")
+        d_cnt = torch.zeros(2, dtype=torch.int64, device="cuda")
+        n0 = m.launch_count
+        if form == "fused":
+            m.loopback_device_into(d_bits, F, 2 * nsym, d_cnt, tx=d_tx, sym=d_sym, bits_out=d_out)
+        else:
+            m.modulate_into(d_bits, F, 2 * nsym, tx=d_tx)
+            m.demodulate_count_into(d_tx, F, L, d_bits, 2 * nsym, d_cnt, sym=d_sym, bits=d_out)
+        torch.cuda.synchronize()
+        assert m.launch_count - n0 == (2 if form == "fused" else 3), form  # + the NCO table
+        assert tuple(d_cnt.tolist()) == (0, F * K * 2), form
+        assert torch.equal(d_out, d_bits[:, : 2 * K])
+        assert torch.equal(d_sym, d_out[:, 0::2] * 2 + d_out[:, 1::2])
+        assert not bool(torch.isnan(d_tx).any()), form
+        res[form] = (d_tx, d_sym)
+        m.close()
+    assert torch.equal(res["fused"][0].view(torch.int32), res["two kernels"][0].view(torch.int32))
+    assert torch.equal(res["fused"][1], res["two kernels"][1])
+    idx = [0, 1, 15, 16, 2047, 4095]
+    tx_ref = o.modulate(d_bits[idx].cpu().numpy())
+    assert_buffers(res["fused"][0][idx].cpu().numpy(), tx_ref, "C1 sampled tx")
+    _, sym_ref, _ = o.demodulate(tx_ref, want_filt=False)
+    assert np.array_equal(res["fused"][1][idx].cpu().numpy(), sym_ref)
+
+
 def test_full_size_c5_bank_properties(pkg, orc):
     """BASELINE config 5 as one GPU carries it: 128 carriers x 32 frames x 65536 samples (frames grouped by channel,
     frames_per_block dividing the channel size), through the fused loopback kernel and through TX + RX: round trip without
