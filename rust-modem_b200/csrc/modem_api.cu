@@ -619,7 +619,7 @@ int launch_loop_fused(modem_ctx* ctx, const uint8_t* d_bits, u64 F, u64 nbits, f
     } else {
         const u64 tiles = (a.K + mg::loop_fused_tile_symbols_64() - 1) / mg::loop_fused_tile_symbols_64();
         a.frames_per_block = std::min<uint32_t>(frames_per_block(ctx, F, tiles), 16);
-        if (ctx->rx_fpb > 0 && !ctx->n_channels) a.frames_per_block = (uint32_t)std::max<u64>(ctx->rx_fpb, (F + 65534) / 65535);
+        if (ctx->rx_fpb > 0) a.frames_per_block = (uint32_t)std::max<u64>(ctx->rx_fpb, (F + 65534) / 65535);
         if (ctx->n_channels) while (ctx->frames_per_channel % a.frames_per_block || ctx->frame_base % a.frames_per_block) --a.frames_per_block;
         a.tile_major = ctx->rx_tile_major == 0 ? 0u : 1u;
     }
