@@ -154,12 +154,26 @@ def test_create_rejects_bad_cfg(pkg):
     assert b"bits_per_symbol" in L.modem_gpu_last_error(None)
 
 
+def test_entries_reject_null_arguments_without_a_device(pkg):
+    """Every compute entry returns an error code for a null context (no abort, no CPU path behind it)."""
+    L = pkg.lib()
+    cnt = (C.c_uint64 * 2)(0, 0)
+    buf = (C.c_uint8 * 16)()
+    assert L.modem_gpu_loopback(None, buf, 1, 16, C.c_float(0.0), 0, 0, None, None, None, cnt) == -1
+    assert L.modem_gpu_loopback_packed(None, buf, 1, 16, C.c_float(0.0), 0, 0, None, cnt) == -1
+    assert L.modem_gpu_loopback_device(None, buf, 1, 16, C.c_float(0.0), 0, 0, None, None, None, None) == -1
+    assert L.modem_gpu_modulate(None, buf, 1, 16, None, None) == -1
+    assert tuple(cnt) == (0, 0)
+
+
 def test_hot_kernels_do_not_spill(pkg):
     """The tuned RX kernel sits at its register cap (128 at 8 CTAs/SM): an innocent change to the argument structs
     once cost 8 bytes of spill and 7 % of its speed.  The ptxas log of the in-tree build is the guard."""
     logdir = os.path.join(ROOT, "rust-modem_b200", "lib")
     hot = [("rx_fast_64.ptxas.log", "_ZN2mg14rx_fast_kernelILi64ELi0ELb0ELb0ELi64ELi8ELi4ELi3ELi64ELb0EEE"),
            ("loop_fused_64.ptxas.log", "_ZN2mg14rx_fast_kernelILi64ELi0ELb0ELb0ELi128ELi4ELi4ELi3ELi64ELb1EEE"),  # the fused loopback
+           ("rx_dec.ptxas.log", "_ZN2mg13rx_dec_kernelILi64ELb0ELb1ELb1EEE"),  # the fused loopback at the reference's default rates
+           ("rx_dec.ptxas.log", "_ZN2mg13rx_dec_kernelILi64ELb0ELb1ELb0EEE"),
            ("tx_fast.ptxas.log", "_ZN2mg19tx_rect_fast_kernelILi2ELb0ELb0EEE"),
            ("tx_fast.ptxas.log", "_ZN2mg21tx_shaped_fast_kernelILi8ELi129ELb1ELi2ELi2EEE")]  # C3 TX, sign-product form
     for fn, sym in hot:
