@@ -6,7 +6,7 @@ import subprocess
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_SO = os.path.join(_HERE, "lib", "libmodem_gpu.so")
+_SO = os.environ.get("MODEM_GPU_LIB") or os.path.join(_HERE, "lib", "libmodem_gpu.so")  # MODEM_GPU_LIB: a tuning build (tools/)
 
 FLAG_FUSED_MAC = 0x1
 FLAG_NO_TMEM = 0x2

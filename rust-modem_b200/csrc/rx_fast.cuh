@@ -478,6 +478,16 @@ __global__ void __launch_bounds__(THREADS, MINB)
             for (int o = tid * 128; o < (int)(vhi_n - vlo_n) * 8; o += THREADS * 128)
                 asm volatile("prefetch.global.L2 [%0];" ::"l"(nxt + o));
         }
+        /* PF 5 = the next frame's tile is pulled INTO L1, one prefetch per 128-byte line, while the FIR runs: phase A of the next
+         * frame then finds its samples ~40 cycles away instead of an L2 round trip (20 % of the 129-tap kernel's stall samples
+         * sat on that wait).  Needs an L1 that holds the next tiles of all resident CTAs (8 x 17 KB): the launcher asks for a
+         * shared-memory carve-out of RX_CARVEOUT % (164 KB for 8 CTAs, 92 KB of L1) instead of the maximum.  Measured at C2 / C3 /
+         * C5: RX 0.488 -> 0.461, 2.66 -> 2.53, 0.500 -> 0.467 ms; with the maximum carve-out (28 KB of L1) it is slower than PF 3. */
+        if (PF == 5 && f + 1 < f1 && !TXF) {
+            const char* nxt = reinterpret_cast<const char*>(frame + a.L + vlo_n);
+            for (int o = tid * 128; o < (int)(vhi_n - vlo_n) * 8; o += THREADS * 128)
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(nxt + o));
+        }
         if (PF == 3 && !TXF && f + 1 < f1 && tid == 0 && vhi_n > vlo_n) {
             const char* nxt = reinterpret_cast<const char*>(frame + a.L + vlo_n);
             asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(nxt), "r"((int)(vhi_n - vlo_n) * 8) : "memory");
@@ -656,7 +666,10 @@ cudaError_t rx_fast_launch_t(const RxArgs& a, const float* h_taps, cudaStream_t 
     if (dev < 0 || dev >= kMaxDevices || configured[dev].load(std::memory_order_acquire) != smem + 1) {
         e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+#ifndef RX_CARVEOUT
+#define RX_CARVEOUT 66 /* per cent of the SM's 228 KB: the 164 KB configuration holds 8 CTAs of the 64-thread shapes */
+#endif
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, PF == 5 ? (int)(RX_CARVEOUT) : (int)cudaSharedmemCarveoutMaxShared);
         if (e != cudaSuccess) return e;
         if (dev >= 0 && dev < kMaxDevices) configured[dev].store(smem + 1, std::memory_order_release);
     }

@@ -14,13 +14,16 @@
 #define RX129_R 4
 #define RX129_TMC 64
 #endif
+#ifndef RX129_PF
+#define RX129_PF RX_DEFAULT_PF
+#endif
 
 namespace mg {
 cudaError_t rx_fast_launch_129n(const RxArgs&, const float*, bool, bool, cudaStream_t);
 cudaError_t rx_fast_launch_129(const RxArgs& a, const float* h_taps, bool fma, bool tmem, cudaStream_t stream)
 {
     if (a.nz.sigma != 0.0f) return rx_fast_launch_129n(a, h_taps, fma, tmem, stream);
-    return rx_fast_dispatch_clean<129, RX129_THREADS, RX129_MINB, RX129_R, RX_DEFAULT_PF, RX129_TMC>(a, h_taps, fma, tmem, stream);
+    return rx_fast_dispatch_clean<129, RX129_THREADS, RX129_MINB, RX129_R, RX129_PF, RX129_TMC>(a, h_taps, fma, tmem, stream);
 }
 uint64_t rx_fast_tiles_129(uint64_t K)
 {

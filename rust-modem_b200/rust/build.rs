@@ -12,7 +12,7 @@ use std::path::PathBuf;
 use std::process::Command;
 
 // keep in step with RXTUNE in csrc/Makefile (checked by tests/test_rust_boundary.py)
-const RXTUNE: [&str; 5] = ["-DRX_DEFAULT_THREADS=64", "-DRX_DEFAULT_MINB=8", "-DRX_DEFAULT_R=4", "-DRX_DEFAULT_PF=3", "-DRX_DEFAULT_TMC=64"];
+const RXTUNE: [&str; 6] = ["-DRX_DEFAULT_THREADS=64", "-DRX_DEFAULT_MINB=8", "-DRX_DEFAULT_R=4", "-DRX_DEFAULT_PF=5", "-DRX_CARVEOUT=66", "-DRX_DEFAULT_TMC=64"];
 
 fn main() {
     let out = PathBuf::from(env::var("OUT_DIR").unwrap());

@@ -111,9 +111,9 @@ def test_build_rs_compiles_what_the_makefile_compiles():
     for u in units:
         assert 'namespace mg' in open(os.path.join(CSRC, u)).read() or u == "modem_api.cu", u
     # ... with the same tuning defines and code-generation flags
-    tune_mk = sorted(re.findall(r"-DRX_DEFAULT_\w+=\d+", re.search(r"RXTUNE\s*\?=\s*(.*)", mk).group(1)))
-    tune_rs = sorted(re.findall(r"-DRX_DEFAULT_\w+=\d+", rs))
-    assert tune_mk == tune_rs and len(tune_mk) == 5
+    tune_mk = sorted(re.findall(r"-DRX_\w+=\d+", re.search(r"RXTUNE\s*\?=\s*(.*)", mk).group(1)))
+    tune_rs = sorted(re.findall(r"-DRX_\w+=\d+", rs))
+    assert tune_mk == tune_rs and len(tune_mk) == 6
     for flag in ("arch=compute_100a,code=sm_100a", "-fmad=false", "-ffp-contract=off", "-std=c++17", "-lineinfo"):
         assert flag in mk and flag in rs, flag
     assert "host_tables.cpp" in mk and "host_tables.cpp" in rs

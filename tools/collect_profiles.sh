@@ -27,7 +27,7 @@ PY
 {
 echo "# ncu --set full --clock-control none --import-source on, one B200 (gpurun), tools/gpu_final.sh: captured after the same command"
 echo "# (python bench.py --steps 2 --warmup 3 --e2e-steps 0 --no-cpu-baseline --configs c1, workload C2) exited 0 without ncu."
-echo "# rx_fast_kernel<..., 128, 4, 4, 3, 64, 1> = the FUSED LOOPBACK kernel (one launch per bench step); tx_rect_fast_kernel and rx_fast_kernel<..., 64, 8, 4, 3, 64, 0> = the two-kernel path timed beside it."
+echo "# rx_fast_kernel<..., 128, 4, 4, 3, 64, 1> = the FUSED LOOPBACK kernel (one launch per bench step); tx_rect_fast_kernel and rx_fast_kernel<..., 64, 8, 4, 5, 64, 0> = the two-kernel path timed beside it."
 echo
 python tools/ncu_summary.py ${O}_c2_prof.ncu-rep
 } > $P/${R}_final_c2_ncu.txt
