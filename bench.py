@@ -555,7 +555,8 @@ def main():
             "metric": "loopback Msamples/s", "value": value, "unit": "Msamples/s", "n_gpus": world,
             "steps": args.steps, "warmup": W, "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": config_block(world, F, {"host_binding": binding}),
+            "config": config_block(world, F),  # exactly the keys and values of the --impl reference line
+            "host_binding": binding,
             "gpu_launches": int(launches),
             "allreduce": {"per_sweep_ms_per_step": ms_per_step, "every_step_ms_per_step": ms_each,
                           "note": "value uses ONE all-reduce of the counters after the K timed steps (inside the timed region); every_step = an all-reduce after each step"},
