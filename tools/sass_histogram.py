@@ -1,13 +1,13 @@
 #!/usr/bin/env python
 """Per-kernel SASS opcode histogram of the built library (cuobjdump -sass): the evidence that the hot kernels are sm_100a
-code using tensor memory (LDTM / STTM), bulk L2 prefetch (UBLKPF), packed binary32 (FMUL2 / FFMA2) and, where the angle
+code using tensor memory (LDTM / STTM), bulk L2 prefetch (UBLKPF), line prefetch into L1 (CCTL.E.PF1), packed binary32 (FMUL2 / FFMA2) and, where the angle
 depends on the data, the binary64 libm (DFMA); and that no tensor-core (UTC*MMA / HMMA) or TMA tile copy (UTMALDG) opcode
 is used -- the path is a stencil, not a GEMM.   usage: sass_histogram.py [lib.so] > profiles/rNN_sass_histogram.txt"""
 import collections, os, re, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 lib = sys.argv[1] if len(sys.argv) > 1 else os.path.join(ROOT, "rust-modem_b200", "lib", "libmodem_gpu.so")
 txt = subprocess.run(["cuobjdump", "-sass", lib], capture_output=True, text=True).stdout
-KEY = ["FMUL2", "FFMA2", "FADD2", "FMUL", "FFMA", "FADD", "DFMA", "DMUL", "DADD", "LDTM", "STTM", "UTCBAR", "UBLKPF", "UTMALDG", "UTMASTG", "UTCHMMA", "UTCQMMA", "HMMA", "IMAD",
+KEY = ["FMUL2", "FFMA2", "FADD2", "FMUL", "FFMA", "FADD", "DFMA", "DMUL", "DADD", "LDTM", "STTM", "UTCBAR", "UBLKPF", "CCTL", "UTMALDG", "UTMASTG", "UTCHMMA", "UTCQMMA", "HMMA", "IMAD",
        "LDG", "STG", "LDS", "STS", "LDC", "LDCU", "SHFL", "BAR", "MUFU", "ATOMG", "RED", "ATOMS"]
 funcs, cur, arch = collections.OrderedDict(), None, None
 for line in txt.splitlines():
