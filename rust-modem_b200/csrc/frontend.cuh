@@ -219,7 +219,7 @@ __global__ void __launch_bounds__(kThreads) cpfsk_table_kernel(float2* tab, u64 
         const u64 v = g / L, n = g % L;
         const float inner = __fmul_rn(__fmul_rn(__fmul_rn(2.0f, (float)(uint32_t)v), p.deviation), __ull2float_rn(sample0 + n + 1));
         float sn, cs;
-        mg_sincosf(inner, &sn, &cs);
+        mg_sincosf_nco(inner, &sn, &cs);
         tab[g] = make_float2(__fmul_rn(p.amplitude, cs), __fmul_rn(p.amplitude, sn));
     }
 }
@@ -301,7 +301,7 @@ __global__ void __launch_bounds__(kThreads) tx_phasor_kernel(const __grid_consta
                         else /* cpfsk.rs:25-31: coef = 2.0 * symbol as f32 */
                             inner = __fmul_rn(__fmul_rn(__fmul_rn(2.0f, (float)sym), p.deviation), sf[u][v]);
                         float s_, c_;
-                        mg_sincosf(inner, &s_, &c_);
+                        mg_sincosf_nco(inner, &s_, &c_);
                         bi = __fmul_rn(p.amplitude, c_);
                         bq = __fmul_rn(p.amplitude, s_);
                     }
@@ -374,7 +374,7 @@ __global__ void __launch_bounds__(64) lock_phase_kernel(const __grid_constant__ 
         /* pll.rs:16-22 */
         const float inner = __fadd_rn(nco_phase(w, a.sample0 + t), po);
         float sn, cs;
-        mg_sincosf(inner, &sn, &cs);
+        mg_sincosf_nco(inner, &sn, &cs);
         const float c_re = cs, c_im = -sn; /* carrier.conj() */
         const float m_re = __fsub_rn(__fmul_rn(x_re, c_re), __fmul_rn(x_im, c_im)); /* num-0.1.35 Complex Mul */
         const float m_im = __fadd_rn(__fmul_rn(x_re, c_im), __fmul_rn(x_im, c_re));

@@ -177,7 +177,7 @@ __global__ void __launch_bounds__(kThreads)
             const float w = ch.w ? __ldg(ch.w + ch0 + c) : ch.w0;
             const float po = with_po ? (ch.po ? __ldg(ch.po + ch0 + c) : ch.po0) : 0.0f;
             float sn, cs;
-            mg_sincosf(__fadd_rn(nco_phase(w, sample0 + n), po), &sn, &cs);
+            mg_sincosf_nco(__fadd_rn(nco_phase(w, sample0 + n), po), &sn, &cs);
             v = make_float2(cs, sn);
         }
         out[g] = v;
@@ -328,7 +328,7 @@ __global__ void __launch_bounds__(kThreads) rx_generic_kernel(const __grid_const
         if (n >= 0 && (u64)n < a.L) {
             const float ph = nco_phase(w, a.sample0 + (u64)n);
             if (pfp) c = ph; /* the frame-invariant part; the offset is added per frame below */
-            else mg_sincosf(__fadd_rn(ph, po), &s, &c);
+            else mg_sincosf_nco(__fadd_rn(ph, po), &s, &c);
         }
         s_cs[j] = make_float2(c, s);
     }
@@ -356,7 +356,7 @@ __global__ void __launch_bounds__(kThreads) rx_generic_kernel(const __grid_const
                 float2 v = make_float2(0.0f, 0.0f);
                 if (ok[u]) {
                     float2 cs = s_cs[j];
-                    if (pfp) mg_sincosf(__fadd_rn(cs.x, pof), &cs.y, &cs.x);
+                    if (pfp) mg_sincosf_nco(__fadd_rn(cs.x, pof), &cs.y, &cs.x);
                     float xv = x[u];
                     if (a.nz.sigma != 0.0f) xv = __fadd_rn(xv, __fmul_rn(a.nz.sigma, noise_re(a.nz, a.nz.frame0 + f, (u64)(nb + j))));
                     v = make_float2(__fmul_rn(xv, cs.x), __fmul_rn(xv, -cs.y)); /* demodulator.rs:53-54 */
@@ -417,7 +417,7 @@ __global__ void __launch_bounds__(kThreads) rx_fullrate_kernel(const __grid_cons
         float2 v = make_float2(0.0f, 0.0f);
         if (n >= 0 && (u64)n < a.L) {
             float s, c;
-            mg_sincosf(__fadd_rn(nco_phase(w, a.sample0 + (u64)n), po), &s, &c);
+            mg_sincosf_nco(__fadd_rn(nco_phase(w, a.sample0 + (u64)n), po), &s, &c);
             v = rx_mix(a, f, a.nz.frame0 + f, (u64)n, c, s);
         }
         s_vi[j] = v.x;

@@ -19,6 +19,10 @@ struct LaunchGeom {
 bool rx_fast_supported(uint32_t n_taps, bool fma, bool tmem);
 uint64_t rx_fast_tiles(uint32_t n_taps, uint64_t K);
 cudaError_t rx_fast_launch(const RxArgs& a, const float* h_taps, bool fma, bool tmem, cudaStream_t stream);
+/* rx_fast_raw.cu: the same kernel fed from real f32 (fmt 1) / i16 (fmt 2) rows with a phase offset per frame */
+bool rx_fast_raw_supported(uint32_t n_taps, uint32_t fmt);
+uint64_t rx_fast_raw_tiles(uint64_t K);
+cudaError_t rx_fast_raw_launch(const RxArgs& a, const float* h_taps, cudaStream_t stream);
 /* fused loopback (loop_fused_64.cu): TX samples made and stored by the demodulating kernel itself */
 uint64_t loop_fused_tile_symbols_64();
 bool loop_fused_supported_64(const RxArgs& a);

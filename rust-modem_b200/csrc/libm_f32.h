@@ -207,6 +207,22 @@ MG_HD void mg_sincosf_0_7(float y, float* sinp, float* cosp)
     mg_sincos_poly(MG_DMUL(x, s), MG_DMUL(x, x), (n & 2) != 0, n, sinp, cosp);
 }
 
+/* The same routine for any |y| < 120 (both signs): glibc's |y| < 120 branch is this very formula, and for |y| < pi/4 it gives
+ * n = 0 and therefore the operands of the small-argument branch -- tools/check_libm.c sweeps every binary32 with |y| < 120
+ * against this machine's sinf / cosf: 0 mismatches (with the signed-zero select below).  Used where the angle is phase(n) + a PLL offset: consecutive samples
+ * of a warp land in different magnitude classes, so the dispatch of mg_sincosf made every warp run every branch. */
+MG_HD void mg_sincosf_lt120(float y, float* sinp, float* cosp)
+{
+    mg_sincosf_0_7(y, sinp, cosp);
+    if (y == 0.0f) *sinp = y; /* sinf(-0) = -0: the one input of the sweep the plain formula gets wrong (it returns +0) */
+}
+/* cos and sin of an NCO angle plus offset: branch-free for |y| < 120, the general routine beyond */
+MG_HD void mg_sincosf_nco(float y, float* sinp, float* cosp)
+{
+    if (mg_abstop12(y) < 0x42f) mg_sincosf_lt120(y, sinp, cosp);
+    else mg_sincosf(y, sinp, cosp);
+}
+
 /* ---- atanf / atan2f ---------------------------------------------------------
  * The reference's PLL takes `(x * carrier.conj()).arg()` (pll.rs:19), i.e. num::Complex::arg =
  * im.atan2(re) -> libm atan2f.  glibc 2.39 still ships the classic fdlibm binary32 routines for

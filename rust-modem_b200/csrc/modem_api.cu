@@ -502,7 +502,18 @@ int launch_rx(modem_ctx* ctx, const float2* d_rx, u64 F, u64 L, uint8_t* d_sym, 
 
     const bool fast_ok = !src && !ctx->force_generic && sps == 8 && c.q_offset == 0 && (L % 2 == 0) && aligned16(d_rx) &&
                          mg::rx_fast_supported(N, fma, !(c.flags & MODEM_FLAG_NO_TMEM));
-    if (fast_ok) {
+    /* the real-valued wire formats of the demodulate binary (f32 / i16 rows, lock samples skipped, one phase offset per
+     * frame): the fast sps-8 kernel with the NCO evaluated per frame (rx_fast_raw.cu).  Without a lock (one offset for the
+     * whole call) the generic kernel, which evaluates the NCO once per CTA, is the faster one: measured */
+    const bool raw_ok = src && src->d_po && !ctx->force_generic && sps == 8 && c.q_offset == 0 && !fma && sigma == 0.0f &&
+                        !(c.flags & MODEM_FLAG_NO_TMEM) && mg::rx_fast_raw_supported(N, src->fmt) && L < (1ull << 31);
+    if (raw_ok) {
+        a.frames_per_block = std::min<uint32_t>(frames_per_block(ctx, F, mg::rx_fast_raw_tiles(a.K)), 16);
+        if (ctx->n_channels) while (ctx->frames_per_channel % a.frames_per_block || ctx->frame_base % a.frames_per_block) --a.frames_per_block;
+        a.tile_major = ctx->rx_tile_major == 0 ? 0u : 1u;
+        set_sign_slicer(ctx, a);
+        CK(ctx, mg::rx_fast_raw_launch(a, ctx->h_rx_taps.data(), ctx->stream));
+    } else if (fast_ok) {
         a.frames_per_block = frames_per_block(ctx, F, mg::rx_fast_tiles(N, a.K));
         if (ctx->rx_fpb > 0 && !ctx->n_channels) a.frames_per_block = (uint32_t)std::max<u64>(ctx->rx_fpb, (F + 65534) / 65535);
         else a.frames_per_block = std::min<uint32_t>(a.frames_per_block, 16); /* measured: 8..16 is the sweet spot once the NCO table removed the per-CTA setup */

@@ -202,12 +202,26 @@ __global__ void __launch_bounds__(THREADS, MINB)
     const long long vhi_n = (u64)(nbase + C::NSAMP) > a.L ? (long long)a.L : nbase + C::NSAMP;
     /* INTERIOR tiles (every staged sample exists in the frame: all but the first and the last tile of a frame) run a
      * phase A without any per-chunk validity test; the noisy and the register-prefetch forms always take the edge form */
-    const bool edge = NOISE || PF == 2 || nbase < 0 || (u64)(nbase + C::NSAMP) > a.L;
+    /* RAW (PF 7 = f32 rows, PF 8 = i16 rows): the real-valued wire of src/bin/demodulate.rs:29-43 with a phase offset that may
+     * differ from frame to frame (Demodulator::lock_phase leaves one in every frame's PLL).  The frame-invariant part of the
+     * NCO angle, phase(n) of carrier.rs:17-19, is what gets parked in tensor memory; every frame adds its own offset and
+     * evaluates cos / sin (libm_f32.h: glibc's, bit for bit) while loading -- demodulator.rs:51-54 as written.  No table, no
+     * prefetch; always the edge form of phase A. */
+    constexpr int RAW = PF == 7 ? 1 : (PF == 8 ? 2 : 0);
+    static_assert(RAW == 0 || (!TXF && !NOISE && TMC > 0), "the raw-wire variant parks its phases in tensor memory");
+    const bool edge = NOISE || PF == 2 || RAW != 0 || nbase < 0 || (u64)(nbase + C::NSAMP) > a.L;
 
     /* NCO values of the tile: read every frame from the zero-padded global table (ChannelView::cs_tab).
      * The tile's 17 KB slice stays L1/L2-resident across the frame loop, costs no shared memory and no
      * setup pass; cs4[q] = (cos, sin) of samples nbase+2q, nbase+2q+1 (zero outside the frame). */
-    const float4* cs4 = reinterpret_cast<const float4*>(chan_table(a.ch, f0) + nbase) + tid;
+    const float4* cs4 = RAW ? nullptr : reinterpret_cast<const float4*>(chan_table(a.ch, f0) + nbase) + tid;
+    const float raw_w = RAW ? chan_w(a.ch, f0) : 0.0f;
+    /* phase(n) of tile-local chunk q's two samples; outside the frame the value is never used (validity mask) */
+    auto raw_phase = [&](int q, float* p0, float* p1) {
+        const long long n = nbase + 2 * (long long)q;
+        *p0 = n >= 0 ? nco_phase(raw_w, a.sample0 + (u64)n) : 0.0f;
+        *p1 = n + 1 >= 0 ? nco_phase(raw_w, a.sample0 + (u64)(n + 1)) : 0.0f;
+    };
     /* TMC columns of tensor memory per thread hold the NCO values of its first TMC/4 chunks */
     constexpr int TCH = TMC / 4;
     __shared__ uint32_t s_tmem;
@@ -222,7 +236,9 @@ __global__ void __launch_bounds__(THREADS, MINB)
             float park[32];
 #pragma unroll
             for (int it = 0; it < 8; ++it) {
-                const float4 t = __ldg(cs4 + (8 * h + it) * THREADS); /* padded table: always readable */
+                float4 t = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                if (RAW) raw_phase((8 * h + it) * THREADS + tid, &t.x, &t.y); /* (phase 0, phase 1, -, -) */
+                else t = __ldg(cs4 + (8 * h + it) * THREADS); /* padded table: always readable */
                 park[4 * it] = t.x; park[4 * it + 1] = t.y; park[4 * it + 2] = t.z; park[4 * it + 3] = t.w;
             }
             tmem_st32(twarp + 32 * h, park); /* column field = bits 15..0 */
@@ -262,15 +278,38 @@ __global__ void __launch_bounds__(THREADS, MINB)
      * the loads below are predicated, never branched around (a branch would make ptxas drain outstanding
      * loads at the join and defeat any prefetch) */
     vmask_t vmask = 0;
+    vmask_t vmask1 = 0; /* RAW: does the chunk's SECOND sample exist?  (a raw frame may hold an odd number of samples) */
 #pragma unroll
     for (int it = 0; it < C::ITER; ++it) {
         const long long n = nbase + 2 * (it * THREADS + tid);
         if (it * THREADS + tid < C::NCHUNK && n >= vlo_n && n < vhi_n) vmask |= (vmask_t)1 << it;
+        if (RAW && it * THREADS + tid < C::NCHUNK && n >= vlo_n && n + 1 < vhi_n) vmask1 |= (vmask_t)1 << it;
     }
     /* does step `it` stage a chunk at all?  Only the last step is partial, and by a compile-time thread count */
     auto staged = [&](int it) { return (it + 1) * THREADS <= C::NCHUNK || tid < C::NCHUNK - it * THREADS; };
+    u64 raw_row = RAW ? f0 * a.raw_stride + a.raw_skip : 0; /* element index of the current frame's sample 0 in a.raw */
     auto load_tile = [&](const float2* fr, auto edge_c) {
         constexpr bool EDGE = decltype(edge_c)::value;
+        if (RAW) { /* one load per sample: rows of the wire may start on any element (odd strides, odd preambles) */
+            const long long e0 = (long long)raw_row + nbase + 2 * tid;
+#pragma unroll
+            for (int it = 0; it < C::ITER; ++it) {
+                const long long e = e0 + 2 * it * THREADS;
+                float x0 = 0.0f, x1 = 0.0f;
+                if (RAW == 1) {
+                    const float* src = reinterpret_cast<const float*>(a.raw);
+                    if (((vmask >> it) & 1) != 0) x0 = __ldg(src + e);
+                    if (((vmask1 >> it) & 1) != 0) x1 = __ldg(src + e + 1);
+                } else { /* `x as f32` of an i16 sample (demodulate.rs:29) */
+                    const short* src = reinterpret_cast<const short*>(a.raw);
+                    if (((vmask >> it) & 1) != 0) x0 = (float)__ldg(src + e);
+                    if (((vmask1 >> it) & 1) != 0) x1 = (float)__ldg(src + e + 1);
+                }
+                xr[it][0] = x0;
+                xr[it][1] = x1;
+            }
+            return;
+        }
         const float4* src = reinterpret_cast<const float4*>(fr + nbase) + tid;
 #pragma unroll
         for (int it = 0; it < C::ITER; ++it) {
@@ -346,6 +385,7 @@ __global__ void __launch_bounds__(THREADS, MINB)
      * frame end (validity bits per chunk), else every chunk exists and only the last step is partial */
     auto phase_a = [&](const float2* fr, u64 f, auto edge_c) {
         constexpr bool EDGE = decltype(edge_c)::value;
+        const float raw_po = RAW ? chan_po(a.ch, f) : 0.0f; /* this frame's PLL.phase_offset (or the call's / the channel's) */
         if (!TXF && PF != 2) load_tile(fr, edge_c);
         if (NOISE) {
             /* AWGN on the fly (oracle/modem_oracle.h "AWGN"): one Philox block serves an aligned QUAD of samples = the chunks
@@ -422,8 +462,18 @@ __global__ void __launch_bounds__(THREADS, MINB)
         for (int it = 0; it < C::ITER; ++it) {
             if (TMC > 0 && it < TCH && it % 8 == 0) tmem_ld32(twarp + 4 * it, parked);
             if (staged(it)) {
-                const float4 cs = (TMC > 0 && it < TCH) ? make_float4(parked[(4 * it) % 32], parked[(4 * it + 1) % 32], parked[(4 * it + 2) % 32], parked[(4 * it + 3) % 32])
-                                                        : LDC(cs4 + it * THREADS);
+                float4 cs;
+                if (RAW) { /* demodulator.rs:51: phase = carrier.next() + pll.phase_offset; :53-54 its cos and sin */
+                    float p0, p1;
+                    if (it < TCH) { p0 = parked[(4 * it) % 32]; p1 = parked[(4 * it + 1) % 32]; }
+                    else raw_phase(it * THREADS + tid, &p0, &p1);
+                    cs = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                    if (((vmask >> it) & 1) != 0) mg_sincosf_nco(__fadd_rn(p0, raw_po), &cs.y, &cs.x);
+                    if (((vmask1 >> it) & 1) != 0) mg_sincosf_nco(__fadd_rn(p1, raw_po), &cs.w, &cs.z);
+                } else {
+                    cs = (TMC > 0 && it < TCH) ? make_float4(parked[(4 * it) % 32], parked[(4 * it + 1) % 32], parked[(4 * it + 2) % 32], parked[(4 * it + 3) % 32])
+                                               : LDC(cs4 + it * THREADS);
+                }
                 float x0r, x1r;
                 if (TXF) {
                     /* (i, q) of the chunk's symbol.  (Fetching these pairs a few steps ahead, or all up front, measured
@@ -460,7 +510,7 @@ __global__ void __launch_bounds__(THREADS, MINB)
         }
     };
     if (PF == 2 && f0 < f1 && !TXF) load_tile(frame, std::true_type{});
-    for (u64 f = f0; f < f1; ++f, orow += a.K, frame += a.L) {
+    for (u64 f = f0; f < f1; ++f, orow += a.K, frame += a.L, raw_row += a.raw_stride) {
         __syncthreads(); /* previous frame's phase B finished; s_slut, s_sq visible */
         if (edge) phase_a(frame, f, std::true_type{});
         else phase_a(frame, f, std::false_type{});

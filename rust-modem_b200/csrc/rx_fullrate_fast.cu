@@ -65,7 +65,7 @@ __global__ void __launch_bounds__(128, 4)
                 nc[i] = t.x;
                 ns[i] = t.y;
             } else {
-                mg_sincosf(__fadd_rn(nco_phase(w, a.sample0 + (u64)n), po0), &ns[i], &nc[i]);
+                mg_sincosf_nco(__fadd_rn(nco_phase(w, a.sample0 + (u64)n), po0), &ns[i], &nc[i]);
             }
         }
     }
@@ -91,7 +91,7 @@ __global__ void __launch_bounds__(128, 4)
                 if (ok[i]) {
                     const float x = xr[i];
                     float c = nc[i], s = ns[i];
-                    if (PFP) mg_sincosf(__fadd_rn(nc[i], po), &s, &c);
+                    if (PFP) mg_sincosf_nco(__fadd_rn(nc[i], po), &s, &c);
                     vi = __fmul_rn(x, c);  /* demodulator.rs:53 */
                     vq = __fmul_rn(x, -s); /* demodulator.rs:54 */
                 }

@@ -201,6 +201,41 @@ def test_demodulate_real_no_lock_uses_cfg_offset(pkg, orc):
     assert_buffers(m.demodulate(z, want_filt=True)["filt"], filt, "complex entry on the same samples")
 
 
+@pytest.mark.parametrize("fmt,lock,delay,pre", [("i16", 64, 35, 64), ("f32", 64, 35, 79), ("i16", 0, 35, 0), ("f32", 64, 36, 64), ("i16", 64, 36, 79),
+                                                ("i16", 64, 35, 39 + 64)])
+def test_bin_path_fast_kernel_sps8(pkg, orc, fmt, lock, delay, pre, monkeypatch):
+    """The demodulate binary's path at 8 samples per symbol through the tuned kernel (rx_fast_raw.cu: real f32 / i16
+    rows, lock samples skipped, one PLL offset per frame, glibc cos / sin evaluated per frame): 23 frames x 3 tiles,
+    odd and even decision delays, against the oracle (offsets, decisions, soft values bit for bit) and against the
+    generic kernel (MODEM_GPU_FORCE_GENERIC)."""
+    sr, br, cf = 10000, 1250, 900
+    bits = rand_bits(47, 23, 2 * 700)
+    # the carrier tone (the lock consumes its first 64 samples), then the data; odd preambles (the reference's sr/cf*pc - 1)
+    # give rows with an odd stride and an odd number of samples behind the lock
+    wire = _wire(orc, bits, br=br, cf=cf, preamble=pre)
+    if lock:  # every frame its own dither on the tone: every frame locks to its own offset
+        wire[:, :lock] += np.random.default_rng(48).integers(-900, 900, (wire.shape[0], lock)).astype(np.int16)
+    x = wire if fmt == "i16" else wire.astype(np.float32) / np.float32(3.0)
+    lp = orc.lowpass_taps()
+    g = 8000.0 if fmt == "i16" else 8000.0 / 3.0
+    delay += pre - lock  # the rest of the tone delays the first symbol
+    kw = dict(scheme="qpsk", baud_rate=br, sample_rate=sr, carrier_hz=cf, rx_taps=lp, decision_delay=delay,
+              slicer_gain=float(np.float32(lp.sum()) * np.float32(g)))
+    m, o = pkg.Modem(**kw), orc.OraclePath(**kw)
+    got = m.demodulate_real(x, lock=lock, want_soft=True, want_filt=False)
+    po, filt, sym, out = o.demodulate_real(x, lock=lock)
+    if lock:
+        assert_buffers(got["phase_offset"], po, "locked phase offsets")
+        assert len(np.unique(po)) > 1
+    assert np.array_equal(got["sym"], sym) and np.array_equal(got["bits"], out)
+    K = sym.shape[1]
+    assert_buffers(got["soft"], np.ascontiguousarray(filt[:, delay::8][:, :K]), "decision-instant soft values")
+    monkeypatch.setenv("MODEM_GPU_FORCE_GENERIC", "1")
+    m2 = pkg.Modem(**kw)
+    ref = m2.demodulate_real(x, lock=lock, want_soft=True, want_filt=False)
+    assert np.array_equal(ref["sym"], got["sym"]) and np.array_equal(ref["soft"].view(np.uint32), got["soft"].view(np.uint32))
+
+
 def test_demodulate_real_short_input(pkg):
     m = pkg.Modem(scheme="qpsk", baud_rate=220, sample_rate=10000, carrier_hz=1000)
     with pytest.raises(pkg.ModemError):  # demodulator.rs:34 unwrap() on None
