@@ -174,6 +174,16 @@ __device__ __forceinline__ uint32_t slice_point_reg4(const float2 (&t)[4], float
     return best;
 }
 
+/* (cos, sin) of an NCO angle plus offset as ONE out-of-line routine: the raw-wire variant evaluates it 34 times per thread and
+ * frame; inlined, those copies made the kernel 5000 instructions long and it stalled on instruction fetch (no_instruction was
+ * its top stall: profiles) */
+static __device__ __noinline__ float2 sincos_nco_call(float y)
+{
+    float s, c;
+    mg_sincosf_nco(y, &s, &c);
+    return make_float2(c, s);
+}
+
 template <int NT, int OFF, bool FMA, bool NOISE, int THREADS, int MINB, int R, int PF, int TMC, bool TXF = false>
 __global__ void __launch_bounds__(THREADS, MINB)
     rx_fast_kernel(const __grid_constant__ RxArgs a, const __grid_constant__ TapsParam<NT> taps)
@@ -302,8 +312,10 @@ __global__ void __launch_bounds__(THREADS, MINB)
                     if (((vmask1 >> it) & 1) != 0) x1 = __ldg(src + e + 1);
                 } else { /* `x as f32` of an i16 sample (demodulate.rs:29) */
                     const short* src = reinterpret_cast<const short*>(a.raw);
-                    if (((vmask >> it) & 1) != 0) x0 = (float)__ldg(src + e);
-                    if (((vmask1 >> it) & 1) != 0) x1 = (float)__ldg(src + e + 1);
+                    /* the integer rides in the float register until the sample is used: converting here would make every thread wait
+                     * for its loads at the top of phase A (long_scoreboard was 2.6 stall cycles per instruction that way) */
+                    if (((vmask >> it) & 1) != 0) x0 = __int_as_float((int)__ldg(src + e));
+                    if (((vmask1 >> it) & 1) != 0) x1 = __int_as_float((int)__ldg(src + e + 1));
                 }
                 xr[it][0] = x0;
                 xr[it][1] = x1;
@@ -468,8 +480,16 @@ __global__ void __launch_bounds__(THREADS, MINB)
                     if (it < TCH) { p0 = parked[(4 * it) % 32]; p1 = parked[(4 * it + 1) % 32]; }
                     else raw_phase(it * THREADS + tid, &p0, &p1);
                     cs = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-                    if (((vmask >> it) & 1) != 0) mg_sincosf_nco(__fadd_rn(p0, raw_po), &cs.y, &cs.x);
-                    if (((vmask1 >> it) & 1) != 0) mg_sincosf_nco(__fadd_rn(p1, raw_po), &cs.w, &cs.z);
+                    /* measured: the f32 wire is faster with the out-of-line routine (1.99 -> 1.68 ms for the bench's 4096 frames: no
+                     * more instruction-fetch stalls), the i16 wire -- whose 2-byte loads arrive late and want the longer inlined
+                     * stretch of work in front of their first use -- with the inlined one (2.02 against 2.21 ms) */
+                    if (RAW == 1) {
+                        if (((vmask >> it) & 1) != 0) { const float2 t = sincos_nco_call(__fadd_rn(p0, raw_po)); cs.x = t.x; cs.y = t.y; }
+                        if (((vmask1 >> it) & 1) != 0) { const float2 t = sincos_nco_call(__fadd_rn(p1, raw_po)); cs.z = t.x; cs.w = t.y; }
+                    } else {
+                        if (((vmask >> it) & 1) != 0) mg_sincosf_nco(__fadd_rn(p0, raw_po), &cs.y, &cs.x);
+                        if (((vmask1 >> it) & 1) != 0) mg_sincosf_nco(__fadd_rn(p1, raw_po), &cs.w, &cs.z);
+                    }
                 } else {
                     cs = (TMC > 0 && it < TCH) ? make_float4(parked[(4 * it) % 32], parked[(4 * it + 1) % 32], parked[(4 * it + 2) % 32], parked[(4 * it + 3) % 32])
                                                : LDC(cs4 + it * THREADS);
@@ -494,6 +514,11 @@ __global__ void __launch_bounds__(THREADS, MINB)
                     /* outside the frame the NCO table holds zeros: x is +-0 there, like the zero the unfused kernel stages */
                     x0r = unpk2(x0).x;
                     x1r = unpk2(x1).x;
+                } else if (RAW == 2) {
+                    /* `x as f32` of the i16 sample (demodulate.rs:29), exact and without a conversion instruction (those share the XU
+                     * pipe with the conversions inside cos / sin): 1.5 * 2^23 + x is the binary32 with the bits 0x4B400000 + x */
+                    x0r = __fsub_rn(__int_as_float(0x4B400000 + __float_as_int(xr[it][0])), 12582912.0f);
+                    x1r = __fsub_rn(__int_as_float(0x4B400000 + __float_as_int(xr[it][1])), 12582912.0f);
                 } else {
                     x0r = xr[it][0];
                     x1r = xr[it][1];
