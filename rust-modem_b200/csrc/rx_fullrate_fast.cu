@@ -19,6 +19,16 @@
 
 namespace mg {
 
+/* (cos, sin) of phase + per-frame offset as one out-of-line routine (see rx_fast.cuh: inlined copies of the binary64 routine
+ * make the kernel stall on instruction fetch) */
+static __device__ __noinline__ float2 sincos_nco_ool(float y)
+{
+    float s, c;
+    mg_sincosf_nco(y, &s, &c);
+    return make_float2(c, s);
+}
+
+
 template <int NT>
 struct FrCfg {
     static constexpr int THREADS = 128;
@@ -91,7 +101,7 @@ __global__ void __launch_bounds__(128, 4)
                 if (ok[i]) {
                     const float x = xr[i];
                     float c = nc[i], s = ns[i];
-                    if (PFP) mg_sincosf_nco(__fadd_rn(nc[i], po), &s, &c);
+                    if (PFP) { const float2 t = sincos_nco_ool(__fadd_rn(nc[i], po)); c = t.x; s = t.y; }
                     vi = __fmul_rn(x, c);  /* demodulator.rs:53 */
                     vq = __fmul_rn(x, -s); /* demodulator.rs:54 */
                 }
