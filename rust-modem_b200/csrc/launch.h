@@ -32,6 +32,9 @@ cudaError_t loop_fused_launch_64(const RxArgs& a, const float* h_taps, bool tmem
 bool rx_dec_supported(uint32_t n_taps, uint32_t sps);
 uint32_t rx_dec_tile_symbols(uint32_t sps);
 cudaError_t rx_dec_launch(const RxArgs& a, const float* h_taps, bool fma, bool tmem, cudaStream_t stream);
+/* the same kernel fed from real f32 (fmt 1) / i16 (fmt 2) rows with a phase offset per frame (rx_dec_kernel<..., 2 / 3>) */
+bool rx_dec_raw_supported(uint32_t n_taps, uint32_t sps, uint32_t fmt);
+cudaError_t rx_dec_raw_launch(const RxArgs& a, const float* h_taps, cudaStream_t stream);
 /* the fused loopback for those shapes (rx_dec_kernel<..., TXF>): QPSK-sized table, rectangular hold, sps <= 64 */
 bool loop_fused_dec_supported(const RxArgs& a);
 cudaError_t loop_fused_dec_launch(const RxArgs& a, const float* h_taps, bool tmem, cudaStream_t stream);

@@ -513,6 +513,13 @@ int launch_rx(modem_ctx* ctx, const float2* d_rx, u64 F, u64 L, uint8_t* d_sym, 
         a.tile_major = ctx->rx_tile_major == 0 ? 0u : 1u;
         set_sign_slicer(ctx, a);
         CK(ctx, mg::rx_fast_raw_launch(a, ctx->h_rx_taps.data(), ctx->stream));
+    } else if (src && src->d_po && !ctx->force_generic && !ctx->no_rx_dec && sps != 8 && c.q_offset == 0 && !fma && sigma == 0.0f &&
+               !(c.flags & MODEM_FLAG_NO_TMEM) && mg::rx_dec_raw_supported(N, sps, src->fmt) && L < (1ull << 31)) {
+        /* the same wire at any other samples-per-symbol count (the reference's own rates: 45): rx_dec_kernel<..., RAW> */
+        a.sym_tile = mg::rx_dec_tile_symbols(sps);
+        a.frames_per_block = frames_per_block(ctx, F, (a.K + a.sym_tile - 1) / a.sym_tile);
+        set_sign_slicer(ctx, a);
+        CK(ctx, mg::rx_dec_raw_launch(a, ctx->h_rx_taps.data(), ctx->stream));
     } else if (fast_ok) {
         a.frames_per_block = frames_per_block(ctx, F, mg::rx_fast_tiles(N, a.K));
         if (ctx->rx_fpb > 0 && !ctx->n_channels) a.frames_per_block = (uint32_t)std::max<u64>(ctx->rx_fpb, (F + 65534) / 65535);

@@ -30,10 +30,26 @@ constexpr int kDecThreads = 128; /* = symbols per tile */
 /* TMEM: the frame-invariant NCO values of a thread's first 32 chunks (128 values) are parked in tensor memory once per CTA
  * (128 columns x 4 CTAs = the SM's 512 columns, all 128 lanes used) and read back with tcgen05.ld every frame, instead of
  * 8 B/sample from the NCO table through L2/L1 next to the 8 B/sample of the signal itself. */
-template <int NT, bool FMA, bool TMEM, bool TXF = false>
+/* (cos, sin) of phase + offset as one out-of-line routine (inlined copies of the binary64 routine stall the kernel on
+ * instruction fetch: rx_fast.cuh) */
+static __device__ __noinline__ float2 dec_sincos_nco(float y)
+{
+    float s, c;
+    mg_sincosf_nco(y, &s, &c);
+    return make_float2(c, s);
+}
+
+/* MODE 0 = complex samples in, 1 = TXF (the fused loopback), 2 / 3 = RAW: the real f32 / i16 wire of src/bin/demodulate.rs:29-43
+ * with one PLL phase offset per frame (Demodulator::lock_phase): the frame-invariant phase(n) is what is parked in tensor
+ * memory, every frame adds its offset and evaluates glibc's cosf / sinf while staging (demodulator.rs:51-54); one load per
+ * sample, because the reference's odd preamble gives rows with odd strides and odd lengths. */
+template <int NT, bool FMA, bool TMEM, int MODE = 0>
 __global__ void __launch_bounds__(kDecThreads, 4)
     rx_dec_kernel(const __grid_constant__ RxArgs a, const __grid_constant__ TapsParam<NT> taps)
 {
+    constexpr bool TXF = MODE == 1;
+    constexpr int RAW = MODE >= 2 ? MODE - 1 : 0; /* 1 = f32 rows, 2 = i16 rows */
+    static_assert(RAW == 0 || (TMEM && !FMA), "the raw-wire variant parks its phases in tensor memory");
     extern __shared__ __align__(16) unsigned char smem_raw[];
     f32x2* s_v = reinterpret_cast<f32x2*>(smem_raw); /* staged (x cos, x sin) pairs, index = sample - nb0 */
     __shared__ float2 s_slut[kMaxLut];
@@ -51,7 +67,8 @@ __global__ void __launch_bounds__(kDecThreads, 4)
     const uint32_t shift = (uint32_t)(nb - nb0);
     const uint32_t R = (TS - 1) * sps + NT + shift; /* samples staged */
     const uint32_t NCH = (R + 1) / 2;               /* 16-byte chunks */
-    const float4* cs4 = reinterpret_cast<const float4*>(chan_table(a.ch, f0) + nb0);
+    const float4* cs4 = RAW ? nullptr : reinterpret_cast<const float4*>(chan_table(a.ch, f0) + nb0);
+    const float raw_w = RAW ? chan_w(a.ch, f0) : 0.0f;
     const f32x2 one = pk2(taps.one.x, taps.one.y);
     const u64 k = k0 + tid;
     const bool live = (uint32_t)tid < TS && k < a.K;
@@ -68,10 +85,16 @@ __global__ void __launch_bounds__(kDecThreads, 4)
     /* the staged chunks that exist in the frame, as a range of chunk indices [vlo, vlo + vspan): L and nb0 are even, so a
      * 16-byte pair is inside the frame or outside; one unsigned compare per chunk */
     const uint32_t vlo = nb0 < 0 ? (uint32_t)((-nb0) >> 1) : 0u;
-    const long long vend = ((long long)a.L - nb0) >> 1; /* first chunk behind the frame's end (> 0: the tile has a live symbol) */
+    /* first chunk behind the frame's end (> 0: the tile has a live symbol); a raw frame may hold an odd number of samples: its
+     * last chunk then has a first sample only (vspan1 covers the chunks whose SECOND sample exists) */
+    const long long vend = ((long long)a.L - nb0 + (RAW ? 1 : 0)) >> 1;
+    const long long vend1 = ((long long)a.L - nb0) >> 1;
     const uint32_t vhi = vend < (long long)NCH ? (uint32_t)(vend < 0 ? 0 : vend) : NCH;
     const uint32_t vspan = vhi > vlo ? vhi - vlo : 0u;
     auto chunk_ok = [&](uint32_t c) { return c - vlo < vspan; };
+    const uint32_t vhi1 = vend1 < (long long)NCH ? (uint32_t)(vend1 < 0 ? 0 : vend1) : NCH;
+    const uint32_t vspan1 = vhi1 > vlo ? vhi1 - vlo : 0u;
+    auto chunk_ok1 = [&](uint32_t c) { return c - vlo < vspan1; };
     /* ---- TXF: the fused loopback for any samples-per-symbol count (the reference's default rates).  Phase A does not load
      * the tile's TX samples, it MAKES them from the frame's bits (a.ref_bits, two bytes per symbol) with the arithmetic of
      * the rectangular-hold TX kernel -- data.rs:66-79 hold, digital/qpsk.rs:23-35 as a 4-entry table (a.tx_iq),
@@ -127,7 +150,16 @@ __global__ void __launch_bounds__(kDecThreads, 4)
 #pragma unroll
             for (int u = 0; u < U; ++u) {
                 const uint32_t c = tid + (b * U + u) * kDecThreads;
-                const float4 t = chunk_ok(c) ? __ldg(cs4 + c) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                float4 t = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                if (chunk_ok(c)) {
+                    if (RAW) { /* (phase 0, phase 1, -, -): carrier.rs:17-19 */
+                        const u64 n = (u64)(nb0 + 2 * (long long)c);
+                        t.x = nco_phase(raw_w, a.sample0 + n);
+                        t.y = nco_phase(raw_w, a.sample0 + n + 1);
+                    } else {
+                        t = __ldg(cs4 + c);
+                    }
+                }
                 park[4 * u] = t.x; park[4 * u + 1] = t.y; park[4 * u + 2] = t.z; park[4 * u + 3] = t.w;
             }
             tmem_st32(twarp + 32 * b, park);
@@ -137,9 +169,34 @@ __global__ void __launch_bounds__(kDecThreads, 4)
     uint32_t err = 0, cmp = 0;
     for (u64 f = f0; f < f1; ++f) {
         __syncthreads(); /* previous frame's FIR finished; s_slut visible */
-        const float4* src = reinterpret_cast<const float4*>(a.rx + f * a.L + nb0);
+        const float4* src = RAW ? nullptr : reinterpret_cast<const float4*>(a.rx + f * a.L + nb0);
+        /* RAW: element index of the frame's sample nb0 in the wire rows, this frame's PLL offset, and the sample loader */
+        const long long raw_e0 = RAW ? (long long)(f * a.raw_stride + a.raw_skip) + nb0 : 0;
+        const float raw_po = RAW ? chan_po(a.ch, f) : 0.0f;
+        auto raw_load = [&](uint32_t c) -> float4 { /* (x0, -, x1, -) like the real parts of a complex pair */
+            float x0 = 0.0f, x1 = 0.0f;
+            const long long e = raw_e0 + 2 * (long long)c;
+            if (RAW == 1) {
+                const float* w = reinterpret_cast<const float*>(a.raw);
+                if (chunk_ok(c)) x0 = __ldg(w + e);
+                if (chunk_ok1(c)) x1 = __ldg(w + e + 1);
+            } else if (RAW == 2) { /* `x as f32` of an i16 sample (demodulate.rs:29) */
+                const short* w = reinterpret_cast<const short*>(a.raw);
+                if (chunk_ok(c)) x0 = (float)__ldg(w + e);
+                if (chunk_ok1(c)) x1 = (float)__ldg(w + e + 1);
+            }
+            return make_float4(x0, 0.0f, x1, 0.0f);
+        };
+        /* RAW: (cos, sin) of the chunk's two samples from their parked phases: phase = carrier.next() + pll.phase_offset
+         * (demodulator.rs:51), evaluated for samples that exist only */
+        auto raw_cs = [&](uint32_t c, float p0, float p1) -> float4 {
+            float4 cs = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+            if (chunk_ok(c)) { const float2 t = dec_sincos_nco(__fadd_rn(p0, raw_po)); cs.x = t.x; cs.y = t.y; }
+            if (chunk_ok1(c)) { const float2 t = dec_sincos_nco(__fadd_rn(p1, raw_po)); cs.z = t.x; cs.w = t.y; }
+            return cs;
+        };
         /* pull the NEXT frame's tile towards L2 while this one is staged and filtered: one bulk (TMA) prefetch per CTA */
-        if (!TXF && tid == 0 && f + 1 < f1) {
+        if (!TXF && !RAW && tid == 0 && f + 1 < f1) {
             const long long lo = nb0 < 0 ? 0 : nb0, hi = min((long long)a.L, nb0 + 2 * (long long)NCH);
             if (hi > lo) {
                 const char* nxt = reinterpret_cast<const char*>(a.rx + (f + 1) * a.L + lo);
@@ -179,7 +236,8 @@ __global__ void __launch_bounds__(kDecThreads, 4)
 #pragma unroll
                         for (int u = 0; u < U; ++u) {
                             const uint32_t c = c0 + u * kDecThreads;
-                            x[u] = chunk_ok(c) ? __ldg(src + c) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                            if (RAW) x[u] = raw_load(c);
+                            else x[u] = chunk_ok(c) ? __ldg(src + c) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
                         }
                     }
                     float parked[32];
@@ -187,7 +245,8 @@ __global__ void __launch_bounds__(kDecThreads, 4)
 #pragma unroll
                     for (int u = 0; u < U; ++u) {
                         const uint32_t c = c0 + u * kDecThreads;
-                        const float4 cs = make_float4(parked[4 * u], parked[4 * u + 1], parked[4 * u + 2], parked[4 * u + 3]);
+                        const float4 cs = RAW ? raw_cs(c, parked[4 * u], parked[4 * u + 1])
+                                              : make_float4(parked[4 * u], parked[4 * u + 1], parked[4 * u + 2], parked[4 * u + 3]);
                         if (FULL || c < NCH) stage(c, TXF ? make_tx(c, cs) : x[u], cs);
                     }
                 };
@@ -201,6 +260,12 @@ __global__ void __launch_bounds__(kDecThreads, 4)
             for (int u = 0; u < U; ++u) {
                 const uint32_t c = c0 + u * kDecThreads;
                 const bool ok = chunk_ok(c);
+                if (RAW) { /* chunks beyond the parked ones (sps > 64): their phases are evaluated here */
+                    x[u] = raw_load(c);
+                    const u64 n = (u64)(nb0 + 2 * (long long)c);
+                    cs[u] = ok ? raw_cs(c, nco_phase(raw_w, a.sample0 + n), nco_phase(raw_w, a.sample0 + n + 1)) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                    continue;
+                }
                 x[u] = (ok && !TXF) ? __ldg(src + c) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
                 cs[u] = ok ? __ldg(cs4 + c) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
             }
@@ -260,11 +325,11 @@ uint32_t rx_dec_tile_symbols(uint32_t sps)
     (void)sps;
     return kDecThreads; /* (127 sps + 66) * 8 B of shared memory: 46 KB at sps 45, 183 KB at sps 180 */
 }
-template <int NT, bool FMA, bool TMEM, bool TXF = false>
+template <int NT, bool FMA, bool TMEM, int MODE = 0>
 static cudaError_t rx_dec_launch_t(const RxArgs& a, const float* h_taps, cudaStream_t stream)
 {
     const size_t smem = ((size_t)(a.sym_tile - 1) * a.sps + NT + 2) * sizeof(f32x2);
-    auto kern = rx_dec_kernel<NT, FMA, TMEM, TXF>;
+    auto kern = rx_dec_kernel<NT, FMA, TMEM, MODE>;
     static std::atomic<size_t> configured[kMaxDevices]; /* per device: the attribute is per device */
     int dev = 0;
     cudaError_t e = cudaGetDevice(&dev);
@@ -302,8 +367,16 @@ bool loop_fused_dec_supported(const RxArgs& a)
 }
 cudaError_t loop_fused_dec_launch(const RxArgs& a, const float* h_taps, bool tmem, cudaStream_t stream)
 {
-    if (tmem) return rx_dec_launch_t<64, false, true, true>(a, h_taps, stream);
-    return rx_dec_launch_t<64, false, false, true>(a, h_taps, stream);
+    if (tmem) return rx_dec_launch_t<64, false, true, 1>(a, h_taps, stream);
+    return rx_dec_launch_t<64, false, false, 1>(a, h_taps, stream);
+}
+/* ---- the demodulate binary's wire at any samples-per-symbol count (the reference's own rates: 45): real f32 (fmt 1) / i16
+ * (fmt 2) rows, one PLL offset per frame */
+bool rx_dec_raw_supported(uint32_t n_taps, uint32_t sps, uint32_t fmt) { return rx_dec_supported(n_taps, sps) && (fmt == 1 || fmt == 2); }
+cudaError_t rx_dec_raw_launch(const RxArgs& a, const float* h_taps, cudaStream_t stream)
+{
+    if (a.rx_fmt == 1) return rx_dec_launch_t<64, false, true, 2>(a, h_taps, stream);
+    return rx_dec_launch_t<64, false, true, 3>(a, h_taps, stream);
 }
 
 } /* namespace mg */

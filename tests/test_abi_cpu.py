@@ -172,8 +172,9 @@ def test_hot_kernels_do_not_spill(pkg):
     logdir = os.path.join(ROOT, "rust-modem_b200", "lib")
     hot = [("rx_fast_64.ptxas.log", "_ZN2mg14rx_fast_kernelILi64ELi0ELb0ELb0ELi64ELi8ELi4ELi5ELi64ELb0EEE"),
            ("loop_fused_64.ptxas.log", "_ZN2mg14rx_fast_kernelILi64ELi0ELb0ELb0ELi128ELi4ELi4ELi3ELi64ELb1EEE"),  # the fused loopback
-           ("rx_dec.ptxas.log", "_ZN2mg13rx_dec_kernelILi64ELb0ELb1ELb1EEE"),  # the fused loopback at the reference's default rates
-           ("rx_dec.ptxas.log", "_ZN2mg13rx_dec_kernelILi64ELb0ELb1ELb0EEE"),
+           ("rx_dec.ptxas.log", "_ZN2mg13rx_dec_kernelILi64ELb0ELb1ELi1EEE"),  # the fused loopback at the reference's default rates
+           ("rx_dec.ptxas.log", "_ZN2mg13rx_dec_kernelILi64ELb0ELb1ELi0EEE"),
+           ("rx_dec.ptxas.log", "_ZN2mg13rx_dec_kernelILi64ELb0ELb1ELi3EEE"),  # the demodulate binary's i16 wire at the reference's rates
            ("tx_fast.ptxas.log", "_ZN2mg19tx_rect_fast_kernelILi2ELb0ELb0EEE"),
            ("tx_fast.ptxas.log", "_ZN2mg21tx_shaped_fast_kernelILi8ELi129ELb1ELi2ELi2EEE")]  # C3 TX, sign-product form
     for fn, sym in hot:

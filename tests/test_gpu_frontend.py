@@ -201,15 +201,18 @@ def test_demodulate_real_no_lock_uses_cfg_offset(pkg, orc):
     assert_buffers(m.demodulate(z, want_filt=True)["filt"], filt, "complex entry on the same samples")
 
 
-@pytest.mark.parametrize("fmt,lock,delay,pre", [("i16", 64, 35, 64), ("f32", 64, 35, 79), ("i16", 0, 35, 0), ("f32", 64, 36, 64), ("i16", 64, 36, 79),
-                                                ("i16", 64, 35, 39 + 64)])
-def test_bin_path_fast_kernel_sps8(pkg, orc, fmt, lock, delay, pre, monkeypatch):
-    """The demodulate binary's path at 8 samples per symbol through the tuned kernel (rx_fast_raw.cu: real f32 / i16
+@pytest.mark.parametrize("fmt,lock,delay,pre,br", [("i16", 64, 35, 64, 1250), ("f32", 64, 35, 79, 1250), ("i16", 0, 35, 0, 1250), ("f32", 64, 36, 64, 1250),
+                                                   ("i16", 64, 36, 79, 1250), ("i16", 64, 35, 39 + 64, 1250),
+                                                   ("i16", 64, 53, 199, 220), ("f32", 64, 53, 64, 220), ("i16", 64, 36, 79, 1000), ("f32", 64, 33, 65, 2000)])
+def test_bin_path_fast_kernel_sps8(pkg, orc, fmt, lock, delay, pre, br, monkeypatch):
+    """The demodulate binary's path through the tuned kernels (sps 8: rx_fast_raw.cu; the reference's own rates, sps 45, and
+    other counts: rx_dec_kernel<..., RAW>): real f32 / i16
     rows, lock samples skipped, one PLL offset per frame, glibc cos / sin evaluated per frame): 23 frames x 3 tiles,
     odd and even decision delays, against the oracle (offsets, decisions, soft values bit for bit) and against the
     generic kernel (MODEM_GPU_FORCE_GENERIC)."""
-    sr, br, cf = 10000, 1250, 900
-    bits = rand_bits(47, 23, 2 * 700)
+    sr, cf = 10000, 900
+    sps = sr // br  # 8: rx_fast_raw.cu; 45 (the reference's own rates), 10, 5: rx_dec_kernel<..., RAW>
+    bits = rand_bits(47, 23, 2 * (700 if sps <= 10 else 300))
     # the carrier tone (the lock consumes its first 64 samples), then the data; odd preambles (the reference's sr/cf*pc - 1)
     # give rows with an odd stride and an odd number of samples behind the lock
     wire = _wire(orc, bits, br=br, cf=cf, preamble=pre)
@@ -229,7 +232,7 @@ def test_bin_path_fast_kernel_sps8(pkg, orc, fmt, lock, delay, pre, monkeypatch)
         assert len(np.unique(po)) > 1
     assert np.array_equal(got["sym"], sym) and np.array_equal(got["bits"], out)
     K = sym.shape[1]
-    assert_buffers(got["soft"], np.ascontiguousarray(filt[:, delay::8][:, :K]), "decision-instant soft values")
+    assert_buffers(got["soft"], np.ascontiguousarray(filt[:, delay::sps][:, :K]), "decision-instant soft values")
     monkeypatch.setenv("MODEM_GPU_FORCE_GENERIC", "1")
     m2 = pkg.Modem(**kw)
     ref = m2.demodulate_real(x, lock=lock, want_soft=True, want_filt=False)

@@ -91,6 +91,39 @@ def demodulate_real(wire_f32, fmt):
     m.close()
 
 
+def demodulate_real_rates(fmt):
+    """The same path at the reference's own rates (sr 10000 / baud 220 -> sps 45, carrier 1000 Hz, preamble of
+    sr / cf * 20 - 1 = 199 samples: modulate.rs:44-58,118-126): 4096 frames x (199 + 65520) samples."""
+    lp = pkg.lowpass_taps()
+    sps, P, nsym = 45, 199, 1456
+    tx = pkg.Modem(scheme="qpsk", baud_rate=220, sample_rate=10000, carrier_hz=1000)
+    st = torch.cuda.current_stream()
+    tx.set_stream(st.cuda_stream)
+    bits = torch.randint(0, 2, (F, 2 * nsym), dtype=torch.uint8, device="cuda")
+    wire = torch.empty((F, P + nsym * sps), dtype=torch.float32, device="cuda")
+    tx._ck(L_.modem_gpu_modulate_real(tx._ctx, bits.data_ptr(), F, 2 * nsym, P, 1.0, wire.data_ptr()))
+    torch.cuda.synchronize()
+    tx.close()
+    m = pkg.Modem(scheme="qpsk", baud_rate=220, sample_rate=10000, carrier_hz=1000, rx_taps=lp,
+                  decision_delay=(P - 64) + 31 + sps // 2, slicer_gain=float(np.float32(lp.sum()) * np.float32(8000.0 if fmt == "i16" else 1.0)))
+    m.set_stream(st.cuda_stream)
+    x = (wire * 8000.0).round().to(torch.int16) if fmt == "i16" else wire
+    Fx, Lx = x.shape
+    Lr = Lx - 64
+    K = m.decided_symbols(Lr)
+    sym = torch.empty((Fx, K), dtype=torch.uint8, device="cuda")
+    out = torch.empty((Fx, K * 2), dtype=torch.uint8, device="cuda")
+    po = torch.empty(Fx, dtype=torch.float32, device="cuda")
+    code = pkg.capi.SAMPLES_I16 if fmt == "i16" else pkg.capi.SAMPLES_F32
+    ms = timeit(lambda: m._ck(L_.modem_gpu_demodulate_real(m._ctx, x.data_ptr(), code, Fx, Lx, 64, None, 0, po.data_ptr(),
+                                                           sym.data_ptr(), out.data_ptr(), None, None)), st)
+    errors = int((out != bits[:, : 2 * K]).sum())
+    n = Fx * Lr
+    print(json.dumps({"row": f"demodulate binary at the reference's own rates (sps 45): {fmt} wire -> Hilbert/PLL lock(64) -> low-pass -> decide",
+                      "ms": round(ms, 4), "Msamples_s": round(n / ms / 1e3), "bit_errors": errors, "po_mean": float(po.mean())}), flush=True)
+    m.close()
+
+
 def fullrate(fmt, Fx=1024):
     """What iterating the reference's Demodulator yields: the filtered (I,Q) for EVERY input sample (demodulator.rs:44-55),
     2 x 64 MACs per sample -- FP32-lane bound by construction (256 lane-ops per sample: <= 145 GS/s exact)."""
@@ -128,6 +161,10 @@ if __name__ == "__main__":
         demodulate_real(w, "i16")
         demodulate_real(w, "f32")
         demodulate_real(w, "f32-nolock")
+        del w
+        torch.cuda.empty_cache()
+        demodulate_real_rates("i16")
+        demodulate_real_rates("f32")
     if "fullrate" in which:
         fullrate("c32")
         fullrate("i16")
