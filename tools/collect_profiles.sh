@@ -10,6 +10,7 @@ cp ${O}_ber_sweep_1gpu.json $P/${R}_ber_sweep_1gpu.json
 cp ${O}_pcie_floor_1gpu.txt $P/${R}_pcie_floor_1gpu.txt
 cp ${O}_packed_sweep.txt $P/${R}_packed_sweep.txt
 cp ${O}_check_sqrt.txt $P/${R}_check_sqrt.txt
+[ -f ${O}_check_sincos_dev.txt ] && cp ${O}_check_sincos_dev.txt $P/${R}_check_sincos_dev.txt
 cp ${O}_launches.csv $P/${R}_final_launches.csv
 python - <<PY > $P/${R}_final_launches.txt
 import csv, collections

@@ -12,6 +12,7 @@ python tools/ber_sweep.py --bits 2e10 > ${O}_ber_sweep_1gpu.json 2> ${O}_ber.err
 python tools/pcie_floor.py > ${O}_pcie_floor_1gpu.txt 2>&1; echo "pcie floor exit $?"
 python tools/packed_sweep.py 256 512 1024 2048 4096 > ${O}_packed_sweep.txt 2>&1; echo "packed sweep exit $?"
 tools/bin/check_sqrt > ${O}_check_sqrt.txt 2>&1; echo "check_sqrt exit $?"
+tools/bin/check_sincos_dev > ${O}_check_sincos_dev.txt 2>&1; echo "check_sincos_dev exit $?"
 CMD="python bench.py --steps 2 --warmup 3 --e2e-steps 0 --no-cpu-baseline --configs c1"
 $CMD > /dev/null 2>&1 && ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file ${O}_launches.csv $CMD > ${O}_ncu_launch.log 2>&1; echo "launch list exit $?"
 # the 12th matching launch is the last fused one of the per-kernel timing loop; the TX / RX pairs of the unfused path follow
