@@ -2,6 +2,7 @@
 # single-GPU evidence of the round (gpurun, one B200): tests, bench line, reference arm, other configs, front-end rows,
 # launch list and ncu --set full of the same bench command (each ncu pass only after the command exited 0 without ncu)
 mkdir -p gpurun_out
+[ -x tools/bin/check_sqrt ] && [ -x tools/bin/check_sincos_dev ] || bash tools/build_tools.sh > gpurun_out/fin_build_tools.log 2>&1
 O=gpurun_out/fin
 python -m pytest tests -q -m gpu > ${O}_pytest.log 2>&1; echo "pytest exit $?"; tail -2 ${O}_pytest.log
 python bench.py > ${O}_bench.json 2> ${O}_bench.err; echo "bench exit $?"
