@@ -33,6 +33,52 @@ __global__ void sums(uint32_t top, uint32_t neg, unsigned long long* out)
     for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
     if ((threadIdx.x & 31) == 0) atomicAdd(out + blockIdx.x, acc);
 }
+__global__ void atan_sums(unsigned long long* out)
+{
+    const uint64_t base = (uint64_t)blockIdx.x * RUN;
+    unsigned long long acc = 0;
+    for (uint32_t i = threadIdx.x; i < RUN; i += blockDim.x) {
+        const uint32_t u = (uint32_t)(base + i);
+        const float r = mg_atanf(__uint_as_float(u));
+        uint32_t rb = __float_as_uint(r);
+        if (r != r) rb = 0x7fc00000u; /* one NaN */
+        acc += fold(rb, 0u, u);
+    }
+    for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0) atomicAdd(out + blockIdx.x, acc);
+}
+/* atanf (the PLL's atan2f is built on it): ALL 2^32 binary32 inputs on the device against glibc's atanf */
+static long check_atan()
+{
+    const uint32_t runs = 1u << 12;
+    unsigned long long* d;
+    cudaMalloc(&d, runs * 8);
+    cudaMemset(d, 0, runs * 8);
+    atan_sums<<<runs, 256>>>(d);
+    std::vector<unsigned long long> got(runs), want(runs, 0);
+    if (cudaMemcpy(got.data(), d, runs * 8, cudaMemcpyDeviceToHost) != cudaSuccess) { printf("CUDA error\n"); return -1; }
+#pragma omp parallel for schedule(dynamic)
+    for (uint32_t r = 0; r < runs; ++r) {
+        unsigned long long acc = 0;
+        for (uint32_t i = 0; i < RUN; ++i) {
+            const uint32_t u = r * RUN + i;
+            float y;
+            memcpy(&y, &u, 4);
+            const float a = atanf(y);
+            uint32_t ab;
+            memcpy(&ab, &a, 4);
+            if (a != a) ab = 0x7fc00000u;
+            acc += fold(ab, 0u, u);
+        }
+        want[r] = acc;
+    }
+    long b = 0;
+    for (uint32_t r = 0; r < runs; ++r) b += got[r] != want[r];
+    printf("mg_atanf (device): all 4294967296 binary32 inputs in %u runs, %ld runs differ from glibc\n", runs, b);
+    cudaFree(d);
+    return b;
+}
+
 int main()
 {
     float lim = 120.0f;
@@ -75,5 +121,6 @@ int main()
             total += top;
         }
     printf("%ld device evaluations against this machine's sinf / cosf: %s\n", total, bad ? "MISMATCH" : "BIT-EXACT");
-    return bad ? 1 : 0;
+    const long ba = check_atan();
+    return (bad || ba) ? 1 : 0;
 }
