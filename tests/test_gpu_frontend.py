@@ -268,3 +268,18 @@ def test_bin_path_many_frames_multichannel(pkg, orc):
     assert_buffers(got["phase_offset"], np.concatenate([r[0] for r in refs]), "bank offsets")
     assert_buffers(got["filt"], np.concatenate([r[1] for r in refs]), "bank (I,Q)")
     assert np.array_equal(got["sym"], np.concatenate([r[2] for r in refs]))
+
+
+def test_device_libm_matches_glibc_exhaustively():
+    """tools/check_sincos_dev.cu: the device's cosf / sinf routines for every binary32 with |y| < 120 (both signs, 4.5e9
+    evaluations) and atanf for all 2^32 inputs against this box's glibc, through per-run checksums."""
+    import os
+    import subprocess
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "tools", "bin", "check_sincos_dev")
+    if not os.path.exists(exe):
+        pytest.skip("tools/bin/check_sincos_dev is not built (tools/build_tools.sh)")
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "BIT-EXACT" in r.stdout and "0 runs differ" in r.stdout.splitlines()[-1]
